@@ -1,0 +1,310 @@
+"""gpmp.core.Model for the exact-GP inner loop on the B200.
+
+Same constructor, method names, argument order and return conventions as gpmp/core/model.py:22-696 for
+the methods on the hot path; the arithmetic of gpmp/core/likelihood.py, linalg.py, kriging.py and
+sample_paths.py is replaced by the device pipelines of libgpmp_b200.so:
+
+  likelihoods   K -> blocked DMMA Cholesky with z and the mean basis whitened as extra rows -> CGS2 of the
+                whitened rows (REML without the n x (n-q) contrast matrix of core/linalg.py:49-88)
+  gradients     T = L^-1, K^-1 = T^T T, M = K^-1 - U^T U, contraction against regenerated dK tiles
+  predict       V = K(xt, xi) L^-T chunk by chunk, row reductions against [Q~; r]; lambda only on request
+
+Two ways in, chosen per call from what the user's covariance callable returns:
+  fused        the callable is a plain gp.kernel.maternp_covariance(x, y, p, param): K is built by the
+               Matern tile kernel inside the pipeline and the gradient never materialises dK;
+  composable   anything else: the callable's own (device) ops build K, the likelihood op returns
+               dvalue/dK = M/2 and autograd continues through the callable.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import torch
+
+from . import _abi, kernel, num, ops
+
+
+def _validate_model_mean(meantype, mean, meanparam):
+    # gpmp/core/utils.py:84-119
+    if meantype not in {"zero", "parameterized", "linear_predictor"}:
+        raise ValueError("meantype must be one of 'zero', 'parameterized', or 'linear_predictor'")
+    if meantype == "zero" and mean is not None:
+        raise ValueError("For meantype 'zero', mean must be None")
+    if meantype in ("parameterized", "linear_predictor") and not callable(mean):
+        raise TypeError("For meantype 'parameterized' or 'linear_predictor', mean must be a callable function")
+
+
+def _ensure_shapes_and_type(xi=None, zi=None, xt=None, convert=True):
+    # gpmp/core/utils.py:19-81
+    if xi is not None:
+        assert len(xi.shape) == 2, "xi should be a 2D array"
+    if zi is not None:
+        if len(zi.shape) == 2:
+            assert zi.shape[1] == 1, "zi should only have one column if it's a 2D array"
+            zi = zi.reshape(-1)
+        else:
+            assert len(zi.shape) == 1, "zi should be 1D or a 2D column array"
+    if xt is not None:
+        assert len(xt.shape) == 2, "xt should be a 2D array"
+    if xi is not None and zi is not None:
+        assert xi.shape[0] == zi.shape[0], "xi and zi must have the same number of rows"
+    if xi is not None and xt is not None:
+        assert xi.shape[1] == xt.shape[1], "xi and xt must have the same number of columns"
+    # device placement is not optional here (convert=False only skips nothing: data must be on the GPU)
+    xi = ops.to_device(xi)
+    zi = ops.to_device(zi)
+    xt = ops.to_device(xt)
+    return xi, zi, xt
+
+
+def _as_param(p):
+    if p is None:
+        return None
+    return num.asparam(p)
+
+
+class Model:
+    """GP model: mean + covariance callables and their parameters (gpmp/core/model.py:136-166)."""
+
+    def __init__(self, mean, covariance, meanparam=None, covparam=None, meantype="linear_predictor"):
+        _validate_model_mean(meantype, mean, meanparam)
+        self.meantype = meantype
+        self.mean = mean
+        self.meanparam = meanparam
+        self.covparam = covparam
+        self.covariance = covariance
+
+    def __repr__(self):
+        return "<gpmp_b200.core.Model object> " + hex(id(self))
+
+    # ------------------------------------------------------------------ helpers
+    def _same_set_cov(self, x, covparam):
+        """K(x, x) from the user's callable, lazily when it is a plain Matern-p covariance."""
+        with kernel.capture():
+            K = self.covariance(x, x, covparam)
+        fused = isinstance(K, kernel.LazyMatern) and K.y is None and K.x is x
+        return K, fused
+
+    def _criterion(self, covparam, xi, zi, P):
+        covparam = _as_param(covparam)
+        K, fused = self._same_set_cov(xi, covparam)
+        try:
+            if fused:
+                return ops.fused_likelihood(K.param, zi, xi, P, K.p)
+            return ops.likelihood_from_K(kernel.materialize(K), zi, P)
+        except torch.linalg.LinAlgError:
+            return num.safe_inf()
+
+    def _basis(self, x, meanparam=None):
+        P = self.mean(x, self.meanparam if meanparam is None else meanparam)
+        P = ops.to_device(P)
+        if P.dim() == 1:
+            P = P.reshape(-1, 1)
+        return P
+
+    # ------------------------------------------------------------------ likelihoods
+    def negative_log_likelihood_zero_mean(self, covparam, xi, zi):
+        """0.5 (n log 2pi + log det K + z^T K^-1 z)  (core/likelihood.py:18-52); +inf when K is not PD."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
+        v = self._criterion(covparam, xi, zi, None)
+        return v.reshape(()) if torch.isfinite(v) else v
+
+    def negative_log_likelihood(self, meanparam, covparam, xi, zi):
+        """Zero-mean NLL of z - mean(x, meanparam) (core/likelihood.py:55-89); differentiable in both."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
+        prior_mean = ops.to_device(self.mean(xi, _as_param(meanparam))).reshape(-1)
+        v = self._criterion(covparam, xi, zi - prior_mean, None)
+        return v.reshape(()) if torch.isfinite(v) else v
+
+    def negative_log_restricted_likelihood(self, covparam, xi, zi):
+        """0.5 ((n-q) log 2pi + log det(W^T K W) + (W^T z)^T (W^T K W)^-1 W^T z)  (core/likelihood.py:92-129),
+        evaluated through the Cholesky-whitened mean basis instead of the contrast matrix W."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
+        P = self._basis(xi)
+        v = self._criterion(covparam, xi, zi, P)
+        return v.reshape(()) if torch.isfinite(v) else v
+
+    # ------------------------------------------------------------------ secondary norms (core/linalg.py:113-141)
+    def norm_k_sqrd_with_zero_mean(self, xi, zi, covparam):
+        """z^T K^-1 z."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
+        state, out = self._fit(xi, zi, None, _as_param(covparam))
+        return torch.tensor(ops.read_small(out)[2], dtype=torch.float64)
+
+    def norm_k_sqrd(self, xi, zi, covparam):
+        """(W^T z)^T (W^T K W)^-1 (W^T z) for the linear-predictor mean."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
+        state, out = self._fit(xi, zi, self._basis(xi), _as_param(covparam))
+        return torch.tensor(ops.read_small(out)[2], dtype=torch.float64)
+
+    # ------------------------------------------------------------------ prediction
+    def _fit(self, xi, zi, P, covparam):
+        """Factor K(xi, xi) with zi (and P) whitened along -> (FitState, out_dev)."""
+        K, fused = self._same_set_cov(xi, covparam)
+        if fused:
+            vals = ops.host_values(K.param)
+            spec = ops._spec_from_param(K.p, xi.shape[1], vals)
+            state, out = ops.lik_value(spec, None, xi, zi, P, False)
+            state.kernel = (K.p, K.param)
+        else:
+            Kd = kernel.materialize(K)
+            Kd = Kd.detach()
+            Kd = Kd if Kd.stride(1) == 1 else Kd.contiguous()
+            state, out = ops.lik_value(None, Kd, None, zi, P, False)
+            state.kernel = None
+        return state, out
+
+    def predict(self, xi, zi, xt, return_lambdas=False, zero_neg_variances=True, convert_in=True,
+                convert_out=True):
+        """Posterior mean / variance at xt given (xi, zi)  (core/model.py:227-307).
+
+        "zero": simple kriging; "linear_predictor": universal kriging with basis mean(x, .);
+        "parameterized": simple kriging of zi - mean(xi, meanparam), prior mean added back.
+        Returns (mean[nt], var[nt]) as NumPy arrays (convert_out) or device tensors, plus the kriging
+        weights lambda_t (ni x nt, device) when return_lambdas.
+        """
+        xi, zi, xt = _ensure_shapes_and_type(xi=xi, zi=zi, xt=xt, convert=convert_in)
+        covparam = _as_param(self.covparam)
+        n, m = xi.shape[0], xt.shape[0]
+        P = Pt = None
+        zt_prior_mean = None
+        zc = zi
+        if self.meantype == "linear_predictor":
+            P = self._basis(xi)
+            Pt = self._basis(xt).contiguous()
+        elif self.meantype == "parameterized":
+            if self.meanparam is None:
+                raise ValueError("For meantype 'parameterized', meanparam should not be None.")
+            mp = _as_param(self.meanparam)
+            zc = zi - ops.to_device(self.mean(xi, mp)).reshape(-1)
+            zt_prior_mean = ops.to_device(self.mean(xt, mp)).reshape(-1)
+        elif self.meantype != "zero":
+            raise ValueError(f"Invalid meantype {self.meantype}.")
+
+        with torch.no_grad():
+            state, out = self._fit(xi, zc, P, covparam)
+            if ops.read_small(out)[6] != 0.0:
+                raise torch.linalg.LinAlgError("predict: K(xi, xi) is not positive-definite")
+            ktt = ops.to_device(self.covariance(xt, None, covparam, pairwise=True)).reshape(-1).contiguous()
+            ld = ops._round_ld(n)
+            chunk = int(max(128, min(32768, (1 << 31) // (8 * ld))))
+            lam_rows = ops._empty((m, ld)) if return_lambdas else None
+            mean = ops._empty((m,))
+            var = ops._empty((m,))
+            for c0 in range(0, m, chunk):
+                c1 = min(m, c0 + chunk)
+                xtc = xt[c0:c1]
+                Vt = lam_rows[c0:c1] if return_lambdas else ops._empty((c1 - c0, ld))
+                fused = state.spec is not None
+                if fused:
+                    with kernel.capture():
+                        Kx = self.covariance(xi, xtc, covparam)
+                    same_kernel = (isinstance(Kx, kernel.LazyMatern) and Kx.y is xtc and Kx.x is xi
+                                   and Kx.p == state.kernel[0] and Kx.param is state.kernel[1])
+                    if not same_kernel:
+                        # the cross-covariance is not the plain Matern of the same-set call: take what the
+                        # callable returns (the solve below only needs K(xt, xi) as rows)
+                        Vt[:, :n].copy_(kernel.materialize(Kx).t())
+                        saved, state.spec = state.spec, None
+                        try:
+                            mu, s2 = ops.predict_chunk(state, xtc, None if Pt is None else Pt[c0:c1],
+                                                       ktt[c0:c1], Vt, return_lambdas)
+                        finally:
+                            state.spec = saved
+                    else:
+                        mu, s2 = ops.predict_chunk(state, xtc, None if Pt is None else Pt[c0:c1], ktt[c0:c1], Vt,
+                                                   return_lambdas)
+                else:
+                    Kx = kernel.materialize(self.covariance(xi, xtc, covparam))
+                    Vt[:, :n].copy_(Kx.t())
+                    mu, s2 = ops.predict_chunk(state, xtc, None if Pt is None else Pt[c0:c1], ktt[c0:c1], Vt,
+                                               return_lambdas)
+                mean[c0:c1] = mu
+                var[c0:c1] = s2
+            if zt_prior_mean is not None:
+                mean = mean + zt_prior_mean
+            if bool((var < 0.0).any()):
+                warnings.warn("Negative variances detected. Consider using jitter.", RuntimeWarning)
+            if zero_neg_variances:
+                var = torch.clamp_min(var, 0.0)
+        if convert_out:
+            mean, var = num.to_np(mean), num.to_np(var)
+        if return_lambdas:
+            return mean, var, lam_rows[:, :n].t()
+        return mean, var
+
+    # ------------------------------------------------------------------ sample paths
+    def sample_paths(self, xt, nb_paths, method="chol", check_result=True):
+        """nb_paths draws of GP(0, k) at xt: C @ N(0, I) with K(xt, xt) = C C^T (core/sample_paths.py:18-63).
+        Only the Cholesky route exists on the device ('svd' is rejected, not emulated)."""
+        if method != "chol":
+            if method == "svd":
+                raise _abi.GpmpError("sample_paths(method='svd') has no device implementation; use 'chol'")
+            raise ValueError("method must be 'chol' or 'svd'")
+        xt_ = ops.to_device(xt)
+        normals = torch.randn(xt_.shape[0], nb_paths, dtype=torch.float64, device=xt_.device,
+                              generator=_generator())
+        return self.sample_paths_from_normals(xt_, normals)
+
+    def sample_paths_from_normals(self, xt, normals):
+        """Deterministic part of sample_paths: C @ normals (the map parity is defined on)."""
+        xt_ = ops.to_device(xt)
+        normals = ops.to_device(normals)
+        with torch.no_grad():
+            K = kernel.materialize(self.covariance(xt_, xt_, _as_param(self.covparam)))
+            fac = ops.potrf(K)  # raises LinAlgError when not PD (the reference checks for NaNs)
+            nt = fac.n
+            L = fac.A[:nt, :nt]
+            Nt = ops.transpose(normals)  # paths x nt
+            return ops.gemm_nt(L, Nt, tri=_abi.TRI_A_LOWER).contiguous()
+
+    def conditional_sample_paths(self, ztsim, xi_ind, zi, xt_ind, lambda_t, convert_out=True):
+        """Conditioning by kriging (core/sample_paths.py:66-119):
+        ztsim[xt_ind] + lambda_t^T (zi - ztsim[xi_ind])."""
+        return self._condition(ztsim, xi_ind, ops.to_device(zi).reshape(-1), xt_ind, lambda_t, None, convert_out)
+
+    def conditional_sample_paths_parameterized_mean(self, ztsim, xi, xi_ind, zi, xt, xt_ind, lambda_t,
+                                                    convert_out=True):
+        """Same with a parameterised prior mean (core/sample_paths.py:122-182)."""
+        xi_, zi_, xt_ = _ensure_shapes_and_type(xi=xi, zi=zi, xt=xt)
+        mp = _as_param(self.meanparam)
+        zc = zi_ - ops.to_device(self.mean(xi_, mp)).reshape(-1)
+        zt_prior = ops.to_device(self.mean(xt_, mp)).reshape(-1, 1)
+        return self._condition(ztsim, xi_ind, zc, xt_ind, lambda_t, zt_prior, convert_out)
+
+    def _condition(self, ztsim, xi_ind, zc, xt_ind, lambda_t, zt_prior, convert_out):
+        with torch.no_grad():
+            zs = ops.to_device(ztsim)
+            dev = zs.device
+            xi_ind = torch.as_tensor(np.asarray(xi_ind).reshape(-1), dtype=torch.long, device=dev)
+            xt_ind = torch.as_tensor(np.asarray(xt_ind).reshape(-1), dtype=torch.long, device=dev)
+            delta = zc.reshape(-1, 1) - zs[xi_ind, :]          # ni x paths
+            out = ops.padded(zs[xt_ind, :])                    # nt x paths (accumulated in place)
+            lam = ops.to_device(lambda_t, requires_contiguous=False)  # ni x nt
+            # rows lambda_t^T (nt x ni): free when lambda_t is the transposed view predict() returns
+            lamT = lam.t()
+            if lamT.stride(1) != 1 or lamT.stride(0) % 2 or lamT.data_ptr() % 16:
+                lamT = ops.transpose(lam)
+            ops.gemm_nt(lamT, ops.transpose(delta), C_out=out, alpha=1.0, beta=1.0)
+            if zt_prior is not None:
+                out = out + zt_prior
+            out = out.contiguous()
+        return num.to_np(out) if convert_out else out
+
+
+_gen = None
+
+
+def _generator():
+    """Backend-global generator seeded 1234, like gpmp/num/torch_backend.py:894-915 (draws themselves are
+    device draws: bit-parity with the CPU generator is not defined)."""
+    global _gen
+    if _gen is None:
+        _gen = torch.Generator(device=ops.device())
+        _gen.manual_seed(1234)
+    return _gen
+
+
+def set_seed(seed):
+    _generator().manual_seed(int(seed))

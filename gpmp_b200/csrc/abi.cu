@@ -1,0 +1,483 @@
+// The C-ABI of libgpmp_b200 (include/gpmp_b200.h): argument checks, workspace layouts and the launch
+// sequences.  Nothing here allocates, synchronises or throws; every call only enqueues on `stream`.
+#include <vector>
+#include "internal.cuh"
+
+namespace gpmp {
+
+// ---- launch accounting / CUDA-event profiling -----------------------------------------------------
+static unsigned long long g_launches = 0;
+static ProfState g_prof = {};
+struct EvPair { cudaEvent_t a, b; };
+static std::vector<EvPair> g_events[KC_COUNT];
+static std::vector<cudaEvent_t> g_pool;
+
+ProfState& prof() { return g_prof; }
+static cudaEvent_t get_event() {
+    if (!g_pool.empty()) {
+        cudaEvent_t e = g_pool.back();
+        g_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int cls, cudaStream_t s) {
+    ++g_launches;
+    if (!g_prof.enabled) return;
+    EvPair p;
+    p.a = get_event();
+    p.b = get_event();
+    cudaEventRecord(p.a, s);
+    g_events[cls].push_back(p);
+}
+void prof_end(int cls, double work, cudaStream_t s) {
+    if (!g_prof.enabled) return;
+    cudaEventRecord(g_events[cls].back().b, s);
+    g_prof.launches[cls] += 1;
+    g_prof.work[cls] += work;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline long long round_ld(int n) { return ((long long)n + 15) / 16 * 16; }
+
+// ---- workspace layouts ---------------------------------------------------------------------------
+struct PotrfWs {
+    int NB, nblk;
+    size_t off_tlo, off_tup, off_w, total;
+};
+static PotrfWs potrf_ws(int n, int nrows) {
+    PotrfWs w;
+    w.NB = potrf_block_size(n);
+    w.nblk = ceil_div(n > 0 ? n : 1, w.NB);
+    size_t tb = (size_t)w.nblk * w.NB * w.NB * 8;
+    w.off_tlo = 0;
+    w.off_tup = align_up(tb, 256);
+    w.off_w = w.off_tup + align_up(tb, 256);
+    size_t wrows = (size_t)(nrows > w.NB ? nrows : w.NB);
+    w.total = w.off_w + align_up(wrows * w.NB * 8, 256);
+    return w;
+}
+
+struct LikWs {
+    int n, q, r, nrows;
+    long long lda;
+    PotrfWs pw;
+    size_t off_A, off_potrf, off_p0rows, off_p0work, off_small, off_U, off_Tlo, off_Tup, off_Kinv, off_partial;
+    size_t total_value, total_grad;
+};
+static LikWs lik_ws(int n, int q, int d) {
+    LikWs w;
+    w.n = n; w.q = q; w.r = q + 1; w.nrows = n + w.r;
+    w.lda = round_ld(n);
+    w.pw = potrf_ws(n, w.nrows);
+    size_t o = 0;
+    w.off_A = o; o += align_up((size_t)(w.nrows + 7) * w.lda * 8, 256);
+    w.off_potrf = o; o += w.pw.total;
+    w.off_p0rows = o; o += align_up((size_t)(q > 0 ? q : 1) * w.lda * 8, 256);
+    w.off_p0work = o; o += align_up((size_t)(q > 0 ? q : 1) * w.lda * 8, 256);
+    w.off_small = o; o += align_up((size_t)(w.r * w.r + 16) * 8, 256);
+    w.off_U = o; o += align_up((size_t)w.r * w.lda * 8, 256);
+    w.total_value = o;
+    w.off_Tlo = o; o += align_up((size_t)n * w.lda * 8, 256);
+    w.off_Tup = o; o += align_up((size_t)n * w.lda * 8, 256);
+    w.off_Kinv = o; o += align_up((size_t)n * w.lda * 8, 256);
+    w.off_partial = o; o += align_up(contract_workspace_bytes(n, n, d > 0 ? d : 1), 256);
+    w.total_grad = o;
+    return w;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace gpmp
+
+using namespace gpmp;
+
+extern "C" {
+
+int gpmp_abi_version(void) { return 1; }
+unsigned long long gpmp_launch_count(void) { return g_launches; }
+
+int gpmp_prof_enable(int enable) {
+    g_prof.enabled = enable ? 1 : 0;
+    return GPMP_OK;
+}
+int gpmp_prof_read(int cls, double* ms, unsigned long long* launches, double* work) {
+    if (cls < 0 || cls >= KC_COUNT) return GPMP_ERR_ARG;
+    double total = 0.0;
+    for (auto& p : g_events[cls]) {
+        if (cudaEventSynchronize(p.b) != cudaSuccess) return GPMP_ERR_CUDA;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, p.a, p.b);
+        total += t;
+        g_pool.push_back(p.a);
+        g_pool.push_back(p.b);
+    }
+    g_events[cls].clear();
+    if (ms) *ms = total;
+    if (launches) *launches = g_prof.launches[cls];
+    if (work) *work = g_prof.work[cls];
+    g_prof.launches[cls] = 0;
+    g_prof.work[cls] = 0.0;
+    return GPMP_OK;
+}
+
+// ---- distances / covariance ---------------------------------------------------------------------
+static int dist_spec(const double* loginvrho, int d, gpmp_cov_spec* s) {
+    if (!loginvrho || d < 1 || d > GPMP_MAX_DIM) return GPMP_ERR_DIM;
+    s->p = 0; s->d = d; s->noise = 0; s->reserved = 0; s->log_sigma2 = 0.0; s->log_tau2 = 0.0;
+    for (int j = 0; j < GPMP_MAX_DIM; ++j) s->loginvrho[j] = j < d ? loginvrho[j] : 0.0;
+    return GPMP_OK;
+}
+
+int gpmp_scaled_distance(const double* loginvrho_host, int d, const double* x_dev, int n, const double* y_dev,
+                         int m, double* D_dev, long long ldd, void* stream) {
+    gpmp_cov_spec s;
+    int rc = dist_spec(loginvrho_host, d, &s);
+    if (rc) return rc;
+    if (!x_dev || !D_dev || n < 0 || m < 0) return GPMP_ERR_ARG;
+    const bool same = (y_dev == nullptr || y_dev == x_dev);
+    return launch_matern_cov(&s, nullptr, 1, 0, x_dev, n, same ? nullptr : y_dev, same ? n : m, D_dev, ldd,
+                             same ? COV_SYM_FULL : COV_RECT, 1, (cudaStream_t)stream);
+}
+
+int gpmp_scaled_distance_elementwise(const double* loginvrho_host, int d, const double* x_dev, const double* y_dev,
+                                     int n, double* out_dev, void* stream) {
+    gpmp_cov_spec s;
+    int rc = dist_spec(loginvrho_host, d, &s);
+    if (rc) return rc;
+    if (!x_dev || !out_dev || n < 0) return GPMP_ERR_ARG;
+    return launch_pairwise(&s, x_dev, y_dev, n, out_dev, 1, (cudaStream_t)stream);
+}
+
+int gpmp_maternp_kernel(int p, const double* h_dev, double* k_dev, double* dk_dev, long long count, void* stream) {
+    if (p < 0 || p > GPMP_MAX_P) return GPMP_ERR_DIM;
+    if (!h_dev || !k_dev || count < 0) return GPMP_ERR_ARG;
+    return launch_maternp_elementwise(p, h_dev, k_dev, dk_dev, count, (cudaStream_t)stream);
+}
+
+int gpmp_matern_cov(const gpmp_cov_spec* spec, const double* x_dev, int n, const double* y_dev, int m,
+                    double* K_dev, long long ldk, int mode, void* stream) {
+    if (!spec || !x_dev || !K_dev || n < 0 || m < 0) return GPMP_ERR_ARG;
+    const bool same = (y_dev == nullptr);
+    int cm;
+    if (same) cm = mode == GPMP_COV_LOWER ? COV_SYM_LOWER : COV_SYM_FULL;
+    else {
+        if (mode != GPMP_COV_FULL) return GPMP_ERR_ARG;
+        cm = COV_RECT;
+    }
+    return launch_matern_cov(spec, nullptr, 1, 0, x_dev, n, y_dev, same ? n : m, K_dev, ldk, cm, 0,
+                             (cudaStream_t)stream);
+}
+
+int gpmp_matern_cov_pairwise(const gpmp_cov_spec* spec, const double* x_dev, const double* y_dev, int n,
+                             double* out_dev, void* stream) {
+    if (!spec || !x_dev || !out_dev || n < 0) return GPMP_ERR_ARG;
+    return launch_pairwise(spec, x_dev, y_dev, n, out_dev, 0, (cudaStream_t)stream);
+}
+
+size_t gpmp_contract_workspace_bytes(int n, int m, int d) { return contract_workspace_bytes(n, m, d); }
+
+int gpmp_matern_cov_backward(const gpmp_cov_spec* spec, const double* x_dev, int n, const double* y_dev, int m,
+                             const double* G_dev, long long ldg, double* grad_dev, void* partial_dev,
+                             size_t partial_bytes, void* stream) {
+    if (!spec || !x_dev || !G_dev || !grad_dev || !partial_dev) return GPMP_ERR_ARG;
+    return launch_contract(spec, x_dev, n, y_dev, y_dev ? m : n, G_dev, ldg, nullptr, 0, 0, 0, 0, 1.0, grad_dev,
+                           partial_dev, partial_bytes, (cudaStream_t)stream);
+}
+
+int gpmp_scaled_distance_backward(const double* loginvrho_host, int d, const double* x_dev, int n,
+                                  const double* y_dev, int m, const double* G_dev, long long ldg, double* grad_dev,
+                                  void* partial_dev, size_t partial_bytes, void* stream) {
+    gpmp_cov_spec s;
+    int rc = dist_spec(loginvrho_host, d, &s);
+    if (rc) return rc;
+    if (!x_dev || !G_dev || !grad_dev || !partial_dev) return GPMP_ERR_ARG;
+    // grad_dev[0] is unused (no sigma2); grad_dev[1..d] = d/d loginvrho_j
+    return launch_contract(&s, x_dev, n, y_dev, y_dev ? m : n, G_dev, ldg, nullptr, 0, 0, 0, 1, 1.0, grad_dev,
+                           partial_dev, partial_bytes, (cudaStream_t)stream);
+}
+
+// ---- Cholesky family ---------------------------------------------------------------------------
+size_t gpmp_potrf_workspace_bytes(int n, int nrows) { return potrf_ws(n, nrows > n ? nrows : n).total; }
+
+int gpmp_potrf(double* A_dev, int n, int nrows, long long lda, void* work_dev, size_t work_bytes, int* info_dev,
+               void* stream) {
+    if (!A_dev || !work_dev || n < 0 || nrows < n || lda < n) return GPMP_ERR_ARG;
+    if ((lda & 1) || !aligned16(A_dev) || !aligned16(work_dev)) return GPMP_ERR_ALIGN;
+    PotrfWs w = potrf_ws(n, nrows);
+    if (work_bytes < w.total) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    return potrf_core(A_dev, lda, 0, n, nrows, w.NB, (double*)(base + w.off_tlo), (double*)(base + w.off_tup), 0,
+                      (double*)(base + w.off_w), 0, info_dev, 0, 1, (cudaStream_t)stream);
+}
+
+int gpmp_potri(const double* L_dev, int n, long long ldl, const void* potrf_work_dev, double* Tlo_dev,
+               double* Tup_dev, double* Kinv_dev, long long ld, void* stream) {
+    if (!L_dev || !potrf_work_dev || !Tlo_dev || !Tup_dev || !Kinv_dev || n < 0 || ld < n) return GPMP_ERR_ARG;
+    if ((ld & 1) || (ldl & 1)) return GPMP_ERR_ALIGN;
+    PotrfWs w = potrf_ws(n, n);
+    const char* base = static_cast<const char*>(potrf_work_dev);
+    return potri_core(L_dev, n, ldl, w.NB, (const double*)(base + w.off_tlo), (const double*)(base + w.off_tup),
+                      Tlo_dev, Tup_dev, Kinv_dev, ld, (cudaStream_t)stream);
+}
+
+int gpmp_trsm_rows(const double* L_dev, int n, long long ldl, const void* potrf_work_dev, double* Bt_dev, int m,
+                   long long ldb, int trans, void* scratch_dev, void* stream) {
+    if (!L_dev || !potrf_work_dev || !Bt_dev || !scratch_dev || n < 0 || m < 0) return GPMP_ERR_ARG;
+    if ((ldl & 1) || (ldb & 1)) return GPMP_ERR_ALIGN;
+    PotrfWs w = potrf_ws(n, n);
+    const char* base = static_cast<const char*>(potrf_work_dev);
+    return trsm_rows_core(L_dev, n, ldl, w.NB, (const double*)(base + w.off_tlo), (const double*)(base + w.off_tup),
+                          Bt_dev, m, ldb, trans, (double*)scratch_dev, (cudaStream_t)stream);
+}
+
+int gpmp_gemm_nt(const double* A_dev, long long lda, const double* B_dev, long long ldb, double* C_dev,
+                 long long ldc, int M, int N, int K, double alpha, double beta, int tri, int lower, void* stream) {
+    if (!A_dev || !B_dev || !C_dev || M < 0 || N < 0 || K < 0 || tri < 0 || tri > 4) return GPMP_ERR_ARG;
+    GemmDesc g = gemm_desc();
+    g.A = A_dev; g.lda = lda; g.B = B_dev; g.ldb = ldb; g.C = C_dev; g.ldc = ldc;
+    g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.krange = tri; g.lower = lower ? 1 : 0;
+    g.reverse = (tri == KR_TO_ROW);
+    return launch_gemm_nt(g, (cudaStream_t)stream);
+}
+
+int gpmp_transpose(const double* in_dev, long long ldi, double* out_dev, long long ldo, int rows, int cols,
+                   void* stream) {
+    if (!in_dev || !out_dev || rows < 0 || cols < 0) return GPMP_ERR_ARG;
+    return launch_transpose(in_dev, ldi, out_dev, ldo, rows, cols, (cudaStream_t)stream);
+}
+
+// ---- likelihoods ---------------------------------------------------------------------------------
+size_t gpmp_lik_workspace_bytes(int n, int q, int d, int want_grad) {
+    if (n < 0 || q < 0 || q > GPMP_MAX_Q) return 0;
+    LikWs w = lik_ws(n, q, d);
+    return want_grad ? w.total_grad : w.total_value;
+}
+
+int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk, const double* x_dev, int n,
+                   const double* z_dev, const double* P_dev, int q, void* work_dev, size_t work_bytes,
+                   double* out_dev, int* info_dev, void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !z_dev || !work_dev || !out_dev || !info_dev) return GPMP_ERR_ARG;
+    if (q > 0 && !P_dev) return GPMP_ERR_ARG;
+    if (!spec && !K_dev) return GPMP_ERR_ARG;
+    if (spec && !x_dev) return GPMP_ERR_ARG;
+    if (!aligned16(work_dev)) return GPMP_ERR_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    LikWs w = lik_ws(n, q, spec ? spec->d : 1);
+    if (work_bytes < w.total_value) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    double* A = (double*)(base + w.off_A);
+    int rc;
+    if (cudaMemsetAsync(info_dev, 0, sizeof(int), s) != cudaSuccess) return GPMP_ERR_CUDA;
+    if (spec) rc = launch_matern_cov(spec, nullptr, 1, 0, x_dev, n, nullptr, n, A, w.lda, COV_SYM_LOWER, 0, s);
+    else rc = launch_copy_lower(K_dev, ldk, A, w.lda, n, s);
+    if (rc) return rc;
+    LoadRowsArgs lr;
+    lr.P = P_dev; lr.z = z_dev; lr.n = n; lr.q = q;
+    lr.rows = A + (long long)n * w.lda; lr.ld = w.lda; lr.stride = 0;
+    lr.p0rows = q > 0 ? (double*)(base + w.off_p0rows) : nullptr; lr.ld0 = w.lda;
+    rc = launch_load_rows(lr, 1, s);
+    if (rc) return rc;
+    char* pb = base + w.off_potrf;
+    rc = potrf_core(A, w.lda, 0, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo), (double*)(pb + w.pw.off_tup), 0,
+                    (double*)(pb + w.pw.off_w), 0, info_dev, 0, 1, s);
+    if (rc) return rc;
+    FinalizeArgs f;
+    f.rows = lr.rows; f.ld = w.lda; f.strideRows = 0;
+    f.p0rows = (double*)(base + w.off_p0rows); f.ld0 = w.lda;
+    f.p0work = (double*)(base + w.off_p0work); f.strideP0 = 0;
+    f.Ldiag = A; f.ldl = w.lda; f.strideL = 0;
+    f.n = n; f.q = q;
+    f.out = out_dev; f.strideOut = 0;
+    f.Rt = (double*)(base + w.off_small); f.strideRt = 0;
+    f.info = info_dev; f.strideInfo = 0;
+    f.ldr0_in = nullptr;
+    return launch_finalize(f, 1, s);
+}
+
+int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, void* work_dev, size_t work_bytes,
+                  double* grad_dev, double* dz_dev, double* dK_dev, long long lddk, void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev) return GPMP_ERR_ARG;
+    if (spec && (!x_dev || !grad_dev)) return GPMP_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    LikWs w = lik_ws(n, q, spec ? spec->d : 1);
+    if (work_bytes < w.total_grad) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    double* A = (double*)(base + w.off_A);
+    char* pb = base + w.off_potrf;
+    double* Tlo = (double*)(base + w.off_Tlo);
+    double* Tup = (double*)(base + w.off_Tup);
+    double* Kinv = (double*)(base + w.off_Kinv);
+    double* U = (double*)(base + w.off_U);
+    int rc = potri_core(A, n, w.lda, w.pw.NB, (const double*)(pb + w.pw.off_tlo), (const double*)(pb + w.pw.off_tup),
+                        Tlo, Tup, Kinv, w.lda, s);
+    if (rc) return rc;
+    URowsArgs u;
+    u.R = A + (long long)n * w.lda; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;
+    u.n = n;
+    rc = launch_urows(u, s);
+    if (rc) return rc;
+    if (spec) {
+        rc = launch_contract(spec, x_dev, n, nullptr, n, Kinv, w.lda, U, w.lda, w.r, 1, 0, 0.5, grad_dev,
+                             base + w.off_partial, w.total_grad - w.off_partial, s);
+        if (rc) return rc;
+    }
+    if (dz_dev) {
+        if (cudaMemcpyAsync(dz_dev, U + (long long)q * w.lda, (size_t)n * 8, cudaMemcpyDeviceToDevice, s) !=
+            cudaSuccess)
+            return GPMP_ERR_CUDA;
+    }
+    if (dK_dev) {
+        DenseGradArgs dg;
+        dg.Kinv = Kinv; dg.ldk = w.lda; dg.U = U; dg.ldu = w.lda; dg.r = w.r; dg.n = n;
+        dg.dK = dK_dev; dg.lddk = lddk; dg.half = 0.5;
+        rc = launch_dense_grad(dg, s);
+        if (rc) return rc;
+    }
+    return GPMP_OK;
+}
+
+// ---- prediction -----------------------------------------------------------------------------------
+size_t gpmp_predict_scratch_bytes(int n, int q, int m) {
+    const int NB = potrf_block_size(n);
+    return align_up((size_t)m * NB * 8, 256) + align_up((size_t)m * (q + 2) * 8, 256);
+}
+
+int gpmp_predict_chunk(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, void* work_dev,
+                       size_t work_bytes, const double* xt_dev, int m, const double* Pt_dev, const double* ktt_dev,
+                       double* Vt_dev, long long ldv, void* scratch_dev, size_t scratch_bytes, double* mean_dev,
+                       double* var_dev, int want_lambda, void* stream) {
+    if (n <= 0 || m < 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !Vt_dev || !scratch_dev || !mean_dev || !var_dev)
+        return GPMP_ERR_ARG;
+    if (spec && (!x_dev || !xt_dev)) return GPMP_ERR_ARG;
+    if (q > 0 && !Pt_dev) return GPMP_ERR_ARG;
+    if (!spec && !ktt_dev) return GPMP_ERR_ARG;
+    if ((ldv & 1) || ldv < n || m > 65535) return GPMP_ERR_ARG;
+    if (scratch_bytes < gpmp_predict_scratch_bytes(n, q, m)) return GPMP_ERR_WORKSPACE;
+    if (m == 0) return GPMP_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    LikWs w = lik_ws(n, q, spec ? spec->d : 1);
+    if (work_bytes < w.total_value) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    double* A = (double*)(base + w.off_A);
+    char* pb = base + w.off_potrf;
+    const double* Tlo_c = (const double*)(pb + w.pw.off_tlo);
+    const double* Tup_c = (const double*)(pb + w.pw.off_tup);
+    double* Wsc = (double*)scratch_dev;
+    double* dots = (double*)((char*)scratch_dev + align_up((size_t)m * w.pw.NB * 8, 256));
+    int rc;
+    if (spec) {
+        rc = launch_matern_cov(spec, nullptr, 1, 0, xt_dev, m, x_dev, n, Vt_dev, ldv, COV_RECT, 0, s);
+        if (rc) return rc;
+    }
+    rc = trsm_rows_core(A, n, w.lda, w.pw.NB, Tlo_c, Tup_c, Vt_dev, m, ldv, 0, Wsc, s);
+    if (rc) return rc;
+    RowDotsArgs rd;
+    rd.V = Vt_dev; rd.ldv = ldv; rd.m = m; rd.n = n; rd.q = q;
+    rd.R = A + (long long)n * w.lda; rd.ldr = w.lda;
+    rd.Rt = (const double*)(base + w.off_small);
+    rd.Pt = Pt_dev; rd.ktt = ktt_dev; rd.ktt_scalar = spec ? exp(spec->log_sigma2) : 0.0;
+    rd.dots = dots; rd.mean = mean_dev; rd.var = var_dev;
+    rc = launch_rowdots(rd, s);
+    if (rc) return rc;
+    if (want_lambda) {
+        rc = launch_wrows(rd, s);
+        if (rc) return rc;
+        rc = trsm_rows_core(A, n, w.lda, w.pw.NB, Tlo_c, Tup_c, Vt_dev, m, ldv, 1, Wsc, s);
+        if (rc) return rc;
+    }
+    return GPMP_OK;
+}
+
+// ---- batched criterion -----------------------------------------------------------------------------
+struct BatchWs {
+    int n, q, r, nrows, NB, nblk;
+    long long lda;
+    size_t per_A, per_T, per_W, per_mdev, per_particle;
+    size_t shared;  // p0rows + p0work + ldr0 + dummy out
+};
+static BatchWs batch_ws(int n, int q) {
+    BatchWs w;
+    w.n = n; w.q = q; w.r = q + 1; w.nrows = n + w.r;
+    w.lda = round_ld(n);
+    w.NB = potrf_block_size(n);
+    w.nblk = ceil_div(n, w.NB);
+    w.per_A = align_up((size_t)(w.nrows + 1) * w.lda * 8, 256);
+    w.per_T = align_up((size_t)w.nblk * w.NB * w.NB * 8, 256);
+    w.per_W = align_up((size_t)(w.nrows > w.NB ? w.nrows : w.NB) * w.NB * 8, 256);
+    w.per_mdev = align_up(sizeof(MaternDev), 256);
+    w.per_particle = w.per_A + 2 * w.per_T + w.per_W + w.per_mdev;
+    w.shared = 2 * align_up((size_t)(q > 0 ? q : 1) * w.lda * 8, 256) + 256 + 256;
+    return w;
+}
+
+size_t gpmp_criterion_batched_bytes(int n, int q, int nbatch) {
+    if (n <= 0 || q < 0 || nbatch <= 0) return 0;
+    BatchWs w = batch_ws(n, q);
+    return w.shared + (size_t)nbatch * w.per_particle;
+}
+
+int gpmp_criterion_batched(const gpmp_cov_spec* spec, const double* theta_dev, int N, const double* x_dev, int n,
+                           const double* z_dev, const double* P_dev, int q, void* work_dev, size_t work_bytes,
+                           double* values_dev, int* info_dev, void* stream) {
+    if (!spec || !theta_dev || !x_dev || !z_dev || !work_dev || !values_dev || !info_dev) return GPMP_ERR_ARG;
+    if (n <= 0 || N < 0 || q < 0 || q > GPMP_MAX_Q || (q > 0 && !P_dev)) return GPMP_ERR_ARG;
+    if (N == 0) return GPMP_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    BatchWs w = batch_ws(n, q);
+    if (work_bytes < w.shared + w.per_particle) return GPMP_ERR_WORKSPACE;
+    long long cap = (long long)((work_bytes - w.shared) / w.per_particle);
+    if (cap > 32768) cap = 32768;
+    if (cap > N) cap = N;
+    char* base = static_cast<char*>(work_dev);
+    size_t rowsb = align_up((size_t)(q > 0 ? q : 1) * w.lda * 8, 256);
+    double* p0rows = (double*)base;
+    double* p0work = (double*)(base + rowsb);
+    double* ldr0 = (double*)(base + 2 * rowsb);
+    char* pbase = base + w.shared;
+    double* A = (double*)pbase;
+    double* Tlo = (double*)(pbase + (size_t)cap * w.per_A);
+    double* Tup = (double*)(pbase + (size_t)cap * (w.per_A + w.per_T));
+    double* W = (double*)(pbase + (size_t)cap * (w.per_A + 2 * w.per_T));
+    MaternDev* mdev = (MaternDev*)(pbase + (size_t)cap * (w.per_A + 2 * w.per_T + w.per_W));
+    const long long sA = (long long)(w.per_A / 8), sT = (long long)(w.per_T / 8), sW = (long long)(w.per_W / 8);
+    int rc;
+    if (cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)N, s) != cudaSuccess) return GPMP_ERR_CUDA;
+    const int w_theta = 1 + spec->noise + spec->d;
+    for (long long c0 = 0; c0 < N; c0 += cap) {
+        const int nb = (int)((N - c0) < cap ? (N - c0) : cap);
+        rc = launch_prep_theta(spec, theta_dev + c0 * w_theta, nb, 1, mdev, s);
+        if (rc) return rc;
+        // MaternDev entries are packed (sizeof), not per_mdev-strided
+        rc = launch_matern_cov(spec, mdev, nb, sA, x_dev, n, nullptr, n, A, w.lda, COV_SYM_LOWER, 0, s);
+        if (rc) return rc;
+        LoadRowsArgs lr;
+        lr.P = P_dev; lr.z = z_dev; lr.n = n; lr.q = q;
+        lr.rows = A + (long long)n * w.lda; lr.ld = w.lda; lr.stride = sA;
+        lr.p0rows = (q > 0 && c0 == 0) ? p0rows : nullptr; lr.ld0 = w.lda;
+        rc = launch_load_rows(lr, nb, s);
+        if (rc) return rc;
+        rc = potrf_core(A, w.lda, sA, n, w.nrows, w.NB, Tlo, Tup, sT, W, sW, info_dev + c0, 1, nb, s);
+        if (rc) return rc;
+        FinalizeArgs f;
+        f.rows = lr.rows; f.ld = w.lda; f.strideRows = sA;
+        f.p0rows = p0rows; f.ld0 = w.lda; f.p0work = p0work; f.strideP0 = 0;
+        f.Ldiag = A; f.ldl = w.lda; f.strideL = sA;
+        f.n = n; f.q = q;
+        f.Rt = nullptr; f.strideRt = 0;
+        f.info = info_dev + c0; f.strideInfo = 1;
+        f.out = values_dev + c0; f.strideOut = 1;
+        f.ldr0_in = q > 0 ? ldr0 : nullptr;
+        if (c0 == 0 && q > 0) {
+            rc = launch_logdet_r0(p0rows, p0work, w.lda, n, q, ldr0, s);
+            if (rc) return rc;
+        }
+        rc = launch_finalize(f, nb, s);
+        if (rc) return rc;
+    }
+    return GPMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Shared device/host helpers for the gpmp_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gpmp_b200.h"
+
+namespace gpmp {
+
+// ---------------------------------------------------------------------------------------------
+// Launch accounting + optional per-class CUDA-event profiling (bench.py reads these through the
+// C-ABI: gpmp_launch_count / gpmp_prof_*).  Profiling brackets each launch of a class with events
+// on the launching stream; it is off by default and never synchronises by itself.
+// ---------------------------------------------------------------------------------------------
+enum KernelClass {
+    KC_MATERN = 0,    // K1 covariance build (bytes)
+    KC_GEMM = 1,      // DMMA NT GEMM / SYRK / TRSM-as-GEMM (flops)
+    KC_POTF2 = 2,     // diagonal-block factor+invert (flops)
+    KC_CONTRACT = 3,  // K4 dK contraction (bytes)
+    KC_SMALL = 4,     // reductions, QR of whitened rows, trmv, misc
+    KC_BATCHED = 5,   // batched small-n criterion
+    KC_COUNT = 6
+};
+
+struct ProfState {
+    int enabled;
+    unsigned long long launches[KC_COUNT];
+    double work[KC_COUNT];  // algorithmic flops or bytes accumulated per class
+};
+ProfState& prof();
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(int cls, double work, cudaStream_t s);
+
+struct LaunchScope {
+    int cls;
+    double work;
+    cudaStream_t s;
+    LaunchScope(int c, double w, cudaStream_t st) : cls(c), work(w), s(st) { prof_begin(c, st); }
+    ~LaunchScope() { prof_end(cls, work, s); }
+};
+
+#define GPMP_CHECK_LAUNCH()                                   \
+    do {                                                      \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess) return GPMP_ERR_CUDA;         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    // native FP64 tensor instruction on sm_100a: SASS DMMA.8x8x4
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte async copy global->shared with zero-fill: copies src_bytes (0..16), zero-fills the rest.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0 (and broadcast through smem to all). blockDim.x <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* red /* >= 33 doubles of smem */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Internal kernel-launch entry points shared across translation units
+// ---------------------------------------------------------------------------------------------
+enum KRange { KR_FULL = 0, KR_FROM_ROW = 1, KR_TO_ROW = 2, KR_FROM_COL = 3, KR_TO_COL = 4 };
+
+struct GemmDesc {
+    // C[M x N] = alpha * A[M x K] * B[N x K]^T + beta * C   (all row-major, "NT": K contiguous)
+    const double* A; long long lda; long long strideA;
+    const double* B; long long ldb; long long strideB;
+    double* C;       long long ldc; long long strideC;
+    double* Ct;      long long ldct; long long strideCt;  // optional mirror: Ct[j][i] = C[i][j]
+    int M, N, K;
+    double alpha, beta;
+    int lower;   // 1: only tiles with tile_col <= tile_row (tile indices taken on the same origin)
+    int krange;  // KRange: trims the K loop at tile granularity for triangular operands
+    int batch;   // blockIdx.z: strideA/B/C/Ct (elements)
+    // second batch level (blockIdx.y), e.g. the block pairs of one level of the triangular inverse
+    int batch2;
+    long long stride2A, stride2B, stride2C, stride2Ct;
+    int reverse;  // visit tiles in reverse order (longest-K tiles first for KR_TO_ROW)
+};
+inline GemmDesc gemm_desc() {
+    GemmDesc g{};
+    g.alpha = 1.0;
+    g.batch = 1;
+    g.batch2 = 1;
+    return g;
+}
+int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream);
+
+}  // namespace gpmp

@@ -1,0 +1,514 @@
+// K1: fused anisotropic scaled-distance + half-integer Matern tile kernel, and K4: the dK-regenerating
+// gradient contraction.  Both use the same 64x64 tile / 4x4 register block: the x and y tiles are
+// pre-scaled by exp(loginvrho) while being staged in shared memory ([dim][point] layout: broadcast /
+// conflict-free reads), distances are direct differences (the SciPy-cdist form the NumPy reference uses,
+// numpy_backend.py:432-436), stores are 16-byte vectors, 256 B contiguous per half-warp.
+#include <math.h>
+#include "internal.cuh"
+
+namespace gpmp {
+
+static void matern_coef(int p, double* out) {
+    // exp of gammaln differences, as kernel/matern.py:59-63 (table: num/shared.py:21-41)
+    for (int i = 0; i < p; ++i)
+        out[i] = exp(lgamma(p + 1.0) - lgamma(2.0 * p + 1.0) + lgamma(p + i + 1.0) - lgamma(i + 1.0) -
+                     lgamma(p - i + 1.0));
+}
+
+int make_matern_dev(const gpmp_cov_spec* s, MaternDev* m, bool same_set) {
+    if (!s) return GPMP_ERR_ARG;
+    if (s->d < 1 || s->d > GPMP_MAX_DIM || s->p < 0 || s->p > GPMP_MAX_P) return GPMP_ERR_DIM;
+    m->p = s->p;
+    m->d = s->d;
+    m->sigma2 = exp(s->log_sigma2);
+    m->diag_add = 0.0;
+    if (same_set) m->diag_add = s->noise ? exp(s->log_tau2) : 10.0 * m->sigma2 * 2.220446049250313e-16;
+    m->c = 2.0 * sqrt(s->p + 0.5);
+    m->dscale = s->p >= 1 ? -(m->c * m->c) / (2.0 * s->p - 1.0) : -m->c;
+    for (int i = 0; i < GPMP_MAX_P; ++i) m->coef[i] = m->coefm1[i] = 0.0;
+    matern_coef(s->p, m->coef);
+    if (s->p >= 1) matern_coef(s->p - 1, m->coefm1);
+    for (int j = 0; j < GPMP_MAX_DIM; ++j) m->invrho[j] = j < s->d ? exp(s->loginvrho[j]) : 0.0;
+    return GPMP_OK;
+}
+
+// Batched parameters: Theta[N][1 + noise + d] (device) -> MaternDev[N].  tmpl carries p, d, c, the
+// polynomial coefficients; only sigma2 / diagonal term / inverse length-scales differ per row.
+struct PrepThetaArgs {
+    MaternDev tmpl; const double* theta; int N, noise, same_set; MaternDev* out;
+};
+__global__ void prep_theta_kernel(const PrepThetaArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const int d = a.tmpl.d, w = 1 + a.noise + d;
+    const double* th = a.theta + (long long)i * w;
+    MaternDev m = a.tmpl;
+    m.sigma2 = exp(th[0]);
+    m.diag_add = 0.0;
+    if (a.same_set) m.diag_add = a.noise ? exp(th[1]) : 10.0 * m.sigma2 * 2.220446049250313e-16;
+    for (int j = 0; j < d; ++j) m.invrho[j] = exp(th[1 + a.noise + j]);
+    a.out[i] = m;
+}
+int launch_prep_theta(const gpmp_cov_spec* spec, const double* theta_dev, int N, int same_set, MaternDev* out,
+                      cudaStream_t stream) {
+    PrepThetaArgs a;
+    int rc = make_matern_dev(spec, &a.tmpl, false);
+    if (rc) return rc;
+    a.theta = theta_dev; a.N = N; a.noise = spec->noise; a.same_set = same_set; a.out = out;
+    LaunchScope scope(KC_SMALL, 0.0, stream);
+    prep_theta_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
+#define GPMP_BIGF (1.7976931348623157e308 / 1000.0)  /* inftobigf, torch_backend.py:500-502 */
+
+// q(t) = 1 + sum_{i<p} a_i u^(p-i), u = 2t, by Horner in u
+__device__ __forceinline__ double matern_poly(const double* __restrict__ a, int p, double u) {
+    double acc = 0.0;
+    for (int i = 0; i < p; ++i) acc = (acc + a[i]) * u;
+    return 1.0 + acc;
+}
+__device__ __forceinline__ double matern_k(const MaternDev& m, double h) {
+    if (isinf(h)) h = GPMP_BIGF;
+    const double t = m.c * h;
+    return exp(-t) * matern_poly(m.coef, m.p, 2.0 * t);
+}
+// k'(h)/h for p >= 1 (finite at 0); for p == 0 returns k'(h) = -c exp(-t) (caller divides by h)
+__device__ __forceinline__ double matern_dk_over_h(const MaternDev& m, double h) {
+    if (isinf(h)) h = GPMP_BIGF;
+    const double t = m.c * h;
+    const double e = exp(-t);
+    if (m.p == 0) return m.dscale * e;
+    return m.dscale * e * matern_poly(m.coefm1, m.p - 1, 2.0 * t);
+}
+
+constexpr int CT = 64;          // tile edge
+constexpr int COV_THREADS = 256;
+
+enum CovMode { CM_RECT = COV_RECT, CM_SYM_FULL = COV_SYM_FULL, CM_SYM_LOWER = COV_SYM_LOWER };
+
+struct CovArgs {
+    MaternDev m;
+    const MaternDev* mdev;  // optional per-batch parameters (device array indexed by blockIdx.z)
+    long long strideK;      // batch stride of K (elements)
+    const double* x; const double* y;
+    double* K; long long ldk;
+    int n, mcols;
+    int mode;       // CovMode
+    int dist_only;  // write the distance instead of the covariance
+    int vec_ok;     // 16-byte stores allowed
+    int tiles_n;
+};
+
+__device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
+    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)(r + 1) * (r + 2) / 2 <= t) ++r;
+    while ((long long)r * (r + 1) / 2 > t) --r;
+    ti = r;
+    tj = t - (int)((long long)r * (r + 1) / 2);
+}
+
+__device__ __forceinline__ void stage_points(double (*s)[CT], const double* __restrict__ pts, int base, int npts,
+                                             const MaternDev& m, int tid) {
+    // s[j][r] = invrho[j] * pts[base + r][j]; coalesced over the row-major (point, dim) array
+    const int d = m.d;
+    for (int e = tid; e < CT * d; e += COV_THREADS) {
+        int r = e / d, j = e - r * d;
+        int gr = base + r;
+        s[j][r] = gr < npts ? m.invrho[j] * pts[(long long)gr * d + j] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a) {
+    __shared__ __align__(16) double xs[GPMP_MAX_DIM][CT];
+    __shared__ __align__(16) double ys[GPMP_MAX_DIM][CT];
+    __shared__ MaternDev msh;
+    if (a.mdev) {
+        const double* src = reinterpret_cast<const double*>(a.mdev + blockIdx.z);
+        double* dst = reinterpret_cast<double*>(&msh);
+        for (int e = threadIdx.x; e < (int)(sizeof(MaternDev) / 8); e += COV_THREADS) dst[e] = src[e];
+        __syncthreads();
+    }
+    const MaternDev& m = a.mdev ? msh : a.m;
+    double* __restrict__ Kb = a.K + (long long)blockIdx.z * a.strideK;
+    int ti, tj;
+    if (a.mode == CM_RECT) {
+        ti = blockIdx.x / a.tiles_n;
+        tj = blockIdx.x - ti * a.tiles_n;
+    } else {
+        tri_decode(blockIdx.x, ti, tj);
+    }
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int r0 = ti * CT, c0 = tj * CT;
+    stage_points(xs, a.x, r0, a.n, m, tid);
+    stage_points(ys, a.y, c0, a.mcols, m, tid);
+    __syncthreads();
+
+    double h2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h2[i][j] = 0.0;
+    for (int j = 0; j < m.d; ++j) {
+        const double2 xa = *reinterpret_cast<const double2*>(&xs[j][ty * 4]);
+        const double2 xb = *reinterpret_cast<const double2*>(&xs[j][ty * 4 + 2]);
+        const double2 ya = *reinterpret_cast<const double2*>(&ys[j][2 * tx]);
+        const double2 yb = *reinterpret_cast<const double2*>(&ys[j][32 + 2 * tx]);
+        const double xr[4] = {xa.x, xa.y, xb.x, xb.y};
+        const double yc[4] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double df = xr[i] - yc[k];
+                h2[i][k] = fma(df, df, h2[i][k]);
+            }
+    }
+    double v[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double h = sqrt(h2[i][k]);
+            v[i][k] = a.dist_only ? h : m.sigma2 * matern_k(m, h);
+        }
+    const bool sym = a.mode != CM_RECT;
+    const bool diag_tile = sym && ti == tj;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = r0 + ty * 4 + i;
+        if (row >= a.n) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int col = c0 + 32 * b + 2 * tx;
+            double v0 = v[i][2 * b], v1 = v[i][2 * b + 1];
+            if (diag_tile && !a.dist_only) {
+                if (col == row) v0 += m.diag_add;
+                if (col + 1 == row) v1 += m.diag_add;
+            }
+            double* kp = Kb + (long long)row * a.ldk + col;
+            const bool lower_only = a.mode == CM_SYM_LOWER && diag_tile;
+            const bool w0 = col < a.mcols && (!lower_only || col <= row);
+            const bool w1 = col + 1 < a.mcols && (!lower_only || col + 1 <= row);
+            if (w0 && w1 && a.vec_ok) {
+                *reinterpret_cast<double2*>(kp) = make_double2(v0, v1);
+            } else {
+                if (w0) kp[0] = v0;
+                if (w1) kp[1] = v1;
+            }
+        }
+    }
+    if (a.mode == CM_SYM_FULL && !diag_tile) {
+        // mirrored tile: K[col][row], each thread owns 4 consecutive rows -> 32 contiguous bytes per col
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = c0 + 32 * (k >> 1) + 2 * tx + (k & 1);
+            if (col >= a.mcols) continue;
+            const int row = r0 + ty * 4;
+            double* kp = Kb + (long long)col * a.ldk + row;
+            if (row + 3 < a.n && a.vec_ok) {
+                *reinterpret_cast<double2*>(kp) = make_double2(v[0][k], v[1][k]);
+                *reinterpret_cast<double2*>(kp + 2) = make_double2(v[2][k], v[3][k]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (row + i < a.n) kp[i] = v[i][k];
+            }
+        }
+    }
+}
+
+// mdev != nullptr: batched over `batch` parameter sets living in device memory (spec then only supplies
+// p and d for the host-side checks); K advances by strideK per batch entry, x / y are shared.
+int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batch, long long strideK,
+                      const double* x, int n, const double* y, int mcols, double* K, long long ldk, int mode,
+                      int dist_only, cudaStream_t stream) {
+    if (n <= 0 || mcols <= 0 || batch <= 0) return GPMP_OK;
+    const bool same = (y == nullptr || y == x) ;
+    if (mode != CM_RECT && !same) return GPMP_ERR_ARG;
+    CovArgs a;
+    int rc = make_matern_dev(spec, &a.m, same && !dist_only);
+    if (rc) return rc;
+    a.mdev = mdev;
+    a.strideK = strideK;
+    a.x = x;
+    a.y = same ? x : y;
+    a.K = K;
+    a.ldk = ldk;
+    a.n = n;
+    a.mcols = same ? n : mcols;
+    a.mode = mode;
+    a.dist_only = dist_only;
+    a.vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+    const int tm = ceil_div(n, CT), tn = ceil_div(a.mcols, CT);
+    a.tiles_n = tn;
+    long long ntiles = mode == CM_RECT ? (long long)tm * tn : (long long)tm * (tm + 1) / 2;
+    double bytes = mode == CM_SYM_LOWER ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
+    bytes += 8.0 * (double)(n + (same ? 0 : a.mcols)) * spec->d;
+    LaunchScope scope(KC_MATERN, bytes * batch, stream);
+    dim3 grid((unsigned)ntiles, 1, (unsigned)batch);
+    matern_cov_kernel<<<grid, COV_THREADS, 0, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise helpers (pairwise covariance, elementwise distance, maternp_kernel on an array)
+// ---------------------------------------------------------------------------------------------
+struct PairArgs {
+    MaternDev m;
+    const double* x; const double* y; double* out; int n; int dist_only;
+};
+__global__ void pairwise_kernel(const PairArgs a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    if (a.y == nullptr) {
+        a.out[i] = a.dist_only ? 0.0 : a.m.sigma2;
+        return;
+    }
+    double h2 = 0.0;
+    for (int j = 0; j < a.m.d; ++j) {
+        // reference: sqrt(sum((invrho * (x - y))**2)) (torch_backend.py:827-828)
+        const double df = a.m.invrho[j] * (a.x[(long long)i * a.m.d + j] - a.y[(long long)i * a.m.d + j]);
+        h2 = fma(df, df, h2);
+    }
+    const double h = sqrt(h2);
+    a.out[i] = a.dist_only ? h : a.m.sigma2 * matern_k(a.m, h);
+}
+
+struct KernArgs {
+    MaternDev m;
+    const double* h; double* k; double* dk; long long count;
+};
+__global__ void maternp_elementwise_kernel(const KernArgs a) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < a.count; i += stride) {
+        const double h = a.h[i];
+        a.k[i] = matern_k(a.m, h);
+        if (a.dk) {
+            const double w = matern_dk_over_h(a.m, h);
+            a.dk[i] = a.m.p == 0 ? w : w * h;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: gradient contraction.  out[0] = sum G_ik Kc_ik, out[1] = tr(G) (same set), out[2+j] =
+// sum G_ik dKc_ik/dloginvrho_j, with Kc = sigma2 k(D) regenerated per tile.  In the symmetric mode
+// G = Kinv - U^T U is assembled on the fly from the lower triangle of Kinv and the r rows of U, and
+// only lower tiles are visited (off-diagonal entries weighted twice).
+// ---------------------------------------------------------------------------------------------
+constexpr int CONTRACT_MAXR = GPMP_MAX_Q + 1;
+
+struct ContractArgs {
+    MaternDev m;
+    const double* x; const double* y;
+    const double* G; long long ldg;
+    const double* Ut; long long ldu; int r;  // optional low-rank correction rows (r x n)
+    int n, mcols, sym, same_set, tiles_n;
+    int dist_only;    // vjp of the scaled distance itself: weight G_ik / h (0 at h == 0)
+    double* partial;  // [nblocks][2 + d]
+};
+
+__global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArgs a) {
+    __shared__ __align__(16) double xs[GPMP_MAX_DIM][CT];
+    __shared__ __align__(16) double ys[GPMP_MAX_DIM][CT];
+    __shared__ double wacc[COV_THREADS / 32][GPMP_MAX_DIM + 2];
+    const MaternDev& m = a.m;
+    int ti, tj;
+    if (a.sym) tri_decode(blockIdx.x, ti, tj);
+    else { ti = blockIdx.x / a.tiles_n; tj = blockIdx.x - ti * a.tiles_n; }
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int r0 = ti * CT, c0 = tj * CT;
+    stage_points(xs, a.x, r0, a.n, m, tid);
+    stage_points(ys, a.y, c0, a.mcols, m, tid);
+    __syncthreads();
+
+    double h2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h2[i][k] = 0.0;
+    for (int j = 0; j < m.d; ++j) {
+        const double2 xa = *reinterpret_cast<const double2*>(&xs[j][ty * 4]);
+        const double2 xb = *reinterpret_cast<const double2*>(&xs[j][ty * 4 + 2]);
+        const double2 ya = *reinterpret_cast<const double2*>(&ys[j][2 * tx]);
+        const double2 yb = *reinterpret_cast<const double2*>(&ys[j][32 + 2 * tx]);
+        const double xr[4] = {xa.x, xa.y, xb.x, xb.y};
+        const double yc[4] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double df = xr[i] - yc[k];
+                h2[i][k] = fma(df, df, h2[i][k]);
+            }
+    }
+    // weights w = G_ik * sigma2 * k'(h)/h (x2 for strictly-lower entries in sym mode)
+    double w[4][4];
+    double sK = 0.0, sTr = 0.0;
+    const bool diag_tile = a.sym && ti == tj;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = r0 + ty * 4 + i;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = c0 + 32 * (k >> 1) + 2 * tx + (k & 1);
+            double gv = 0.0, mult = 1.0;
+            bool live = row < a.n && col < a.mcols;
+            if (a.sym) {
+                if (diag_tile && col > row) live = false;
+                if (col < row) mult = 2.0;
+            }
+            if (live) {
+                gv = a.G[(long long)row * a.ldg + col];
+                for (int q = 0; q < a.r; ++q) gv -= a.Ut[(long long)q * a.ldu + row] * a.Ut[(long long)q * a.ldu + col];
+            }
+            const double h = sqrt(h2[i][k]);
+            double dkh, kc;
+            if (a.dist_only) {
+                dkh = h > 0.0 ? 1.0 / h : 0.0;  // reference: custom_sqrt has zero gradient at 0
+                kc = 0.0;
+            } else {
+                dkh = matern_dk_over_h(m, h);
+                if (m.p == 0) dkh = h > 0.0 ? dkh / h : 0.0;  // reference: masked sqrt gradient at 0
+                kc = m.sigma2 * matern_k(m, h);
+            }
+            sK += mult * gv * kc;
+            if (a.same_set && live && row == col) sTr += gv;
+            w[i][k] = live ? mult * gv * m.sigma2 * dkh : 0.0;
+        }
+    }
+    // per-dimension sums: warp-reduce each, lane 0 keeps the warp's running value in smem
+    {
+        double t0 = warp_sum(sK), t1 = warp_sum(sTr);
+        if (lane == 0) { wacc[warp][0] = t0; wacc[warp][1] = t1; }
+    }
+    for (int j = 0; j < m.d; ++j) {
+        const double2 xa = *reinterpret_cast<const double2*>(&xs[j][ty * 4]);
+        const double2 xb = *reinterpret_cast<const double2*>(&xs[j][ty * 4 + 2]);
+        const double2 ya = *reinterpret_cast<const double2*>(&ys[j][2 * tx]);
+        const double2 yb = *reinterpret_cast<const double2*>(&ys[j][32 + 2 * tx]);
+        const double xr[4] = {xa.x, xa.y, xb.x, xb.y};
+        const double yc[4] = {ya.x, ya.y, yb.x, yb.y};
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double df = xr[i] - yc[k];
+                s = fma(w[i][k], df * df, s);
+            }
+        s = warp_sum(s);
+        if (lane == 0) wacc[warp][2 + j] = s;
+    }
+    __syncthreads();
+    if (tid < 2 + m.d) {
+        double t = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < COV_THREADS / 32; ++wv) t += wacc[wv][tid];
+        a.partial[(long long)blockIdx.x * (2 + m.d) + tid] = t;
+    }
+}
+
+// deterministic final reduction of the per-tile partials and assembly of d value / d covparam
+struct ContractFinalArgs {
+    const double* partial; long long nblocks; int d, noise;
+    double diag_add, half;  // half = 0.5 for the likelihood (0.5 tr(M dK)), 1.0 for a plain vjp
+    double* grad;           // [1 + noise + d]
+};
+__global__ void contract_final_kernel(const ContractFinalArgs a) {
+    __shared__ double red[40];
+    const int nv = 2 + a.d;
+    __shared__ double tot[GPMP_MAX_DIM + 2];
+    for (int v = 0; v < nv; ++v) {
+        double s = 0.0;
+        for (long long b = threadIdx.x; b < a.nblocks; b += blockDim.x) s += a.partial[b * nv + v];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) tot[v] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (a.noise) {
+            a.grad[0] = a.half * tot[0];
+            a.grad[1] = a.half * a.diag_add * tot[1];
+        } else {
+            a.grad[0] = a.half * (tot[0] + a.diag_add * tot[1]);
+        }
+        for (int j = 0; j < a.d; ++j) a.grad[1 + a.noise + j] = a.half * tot[2 + j];
+    }
+}
+
+size_t contract_workspace_bytes(int n, int mcols, int d) {
+    long long tm = ceil_div(n, CT), tn = ceil_div(mcols, CT);
+    return (size_t)(tm * tn) * (2 + d) * sizeof(double);
+}
+
+int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const double* y, int mcols, const double* G,
+                    long long ldg, const double* Ut, long long ldu, int r, int sym, int dist_only, double half,
+                    double* grad, void* partial, size_t partial_bytes, cudaStream_t stream) {
+    const bool same = (y == nullptr || y == x);
+    if (sym && !same) return GPMP_ERR_ARG;
+    if (r > CONTRACT_MAXR) return GPMP_ERR_ARG;
+    ContractArgs a;
+    int rc = make_matern_dev(spec, &a.m, same);
+    if (rc) return rc;
+    a.x = x; a.y = same ? x : y;
+    a.G = G; a.ldg = ldg; a.Ut = Ut; a.ldu = ldu; a.r = r;
+    a.n = n; a.mcols = same ? n : mcols; a.sym = sym; a.same_set = (same && !dist_only) ? 1 : 0;
+    a.dist_only = dist_only;
+    const int tm = ceil_div(n, CT), tn = ceil_div(a.mcols, CT);
+    a.tiles_n = tn;
+    long long nblocks = sym ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
+    if ((size_t)nblocks * (2 + spec->d) * sizeof(double) > partial_bytes) return GPMP_ERR_WORKSPACE;
+    a.partial = static_cast<double*>(partial);
+    {
+        double bytes = sym ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
+        LaunchScope scope(KC_CONTRACT, bytes, stream);
+        contract_kernel<<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a);
+        GPMP_CHECK_LAUNCH();
+    }
+    ContractFinalArgs f;
+    f.partial = a.partial; f.nblocks = nblocks; f.d = spec->d; f.noise = spec->noise;
+    f.diag_add = a.m.diag_add; f.half = half; f.grad = grad;
+    {
+        LaunchScope scope(KC_SMALL, 0.0, stream);
+        contract_final_kernel<<<1, 256, 0, stream>>>(f);
+        GPMP_CHECK_LAUNCH();
+    }
+    return GPMP_OK;
+}
+
+int launch_pairwise(const gpmp_cov_spec* spec, const double* x, const double* y, int n, double* out, int dist_only,
+                    cudaStream_t stream) {
+    if (n <= 0) return GPMP_OK;
+    PairArgs a;
+    int rc = make_matern_dev(spec, &a.m, false);
+    if (rc) return rc;
+    a.x = x; a.y = (y == x) ? nullptr : y; a.out = out; a.n = n; a.dist_only = dist_only;
+    LaunchScope scope(KC_SMALL, 0.0, stream);
+    pairwise_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
+int launch_maternp_elementwise(int p, const double* h, double* k, double* dk, long long count, cudaStream_t stream) {
+    if (count <= 0) return GPMP_OK;
+    gpmp_cov_spec s;
+    s.p = p; s.d = 1; s.noise = 0; s.reserved = 0; s.log_sigma2 = 0.0; s.log_tau2 = 0.0;
+    for (int j = 0; j < GPMP_MAX_DIM; ++j) s.loginvrho[j] = 0.0;
+    KernArgs a;
+    int rc = make_matern_dev(&s, &a.m, false);
+    if (rc) return rc;
+    a.h = h; a.k = k; a.dk = dk; a.count = count;
+    long long blocks = ceil_div_ll(count, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    LaunchScope scope(KC_SMALL, 0.0, stream);
+    maternp_elementwise_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
+}  // namespace gpmp

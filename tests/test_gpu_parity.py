@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via gpmp_b200) against the committed golden
+vectors of the real reference (tests/golden/) and against the CPU oracle on seeded inputs.
+
+Tolerances are BASELINE.json's: covariance rel-err <= 1e-12, logL and gradient <= 1e-8 relative,
+predictive mean / variance <= 1e-9 (relative to the prior scale sigma).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr, relerr_norm
+from oracle import cases, gp_numpy as onp
+
+pytestmark = pytest.mark.gpu
+
+TOL_COV = 1e-12
+TOL_LIK = 1e-8
+TOL_PRED = 1e-9
+
+
+@pytest.fixture(scope="module")
+def gp():
+    import gpmp_b200
+
+    assert torch.cuda.is_available(), "these tests need the B200"
+    gpmp_b200._abi.lib()  # fail loudly if the native library is missing
+    return gpmp_b200
+
+
+def _cov_callable(gp, p, noise):
+    if not noise:
+        return lambda x, y, cp, pairwise=False: gp.kernel.maternp_covariance(x, y, p, cp, pairwise)
+    gnp = gp.num
+
+    def k(x, y, cp, pairwise=False):
+        # examples/gpmp_example07_nd_regression.py:95-130: sigma2 k_p(D) + tau2 I composed by the user
+        s2, t2, lir = torch.exp(cp[0]), torch.exp(cp[1]), cp[2:]
+        if y is x or y is None:
+            if pairwise:
+                return (s2 + t2) * gnp.ones((x.shape[0],))
+            D = gnp.scaled_distance(lir, x, x)
+            return s2 * gp.kernel.maternp_kernel(p, D) + t2 * gnp.eye(x.shape[0])
+        if pairwise:
+            return s2 * gp.kernel.maternp_kernel(p, gnp.scaled_distance_elementwise(lir, x, y))
+        return s2 * gp.kernel.maternp_kernel(p, gnp.scaled_distance(lir, x, y))
+
+    return k
+
+
+def _model(gp, kind, p, noise, th):
+    mp = cases.MEANPARAM if kind == "param" else None
+    return gp.core.Model(cases.mean_fn(kind, gp.num), _cov_callable(gp, p, noise), mp, th, cases.meantype_of(kind))
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [c[0] for c in cases.COV_CASES])
+def test_covariance(gp, golden_np, case):
+    g = golden_np(case)
+    x, y, th, p = g["x"], g["y"], g["theta"], int(g["p"])
+    gnp = gp.num
+    xd, yd = gnp.asarray(x), gnp.asarray(y)
+    k = min(len(x), len(y))
+    D = gnp.scaled_distance(th[1:], xd, yd).cpu().numpy()
+    assert relerr_norm(D, g["D"]) <= TOL_COV
+    Dxx = gnp.scaled_distance(th[1:], xd, xd).cpu().numpy()
+    assert np.all(np.diag(Dxx) == 0.0) and relerr_norm(Dxx, g["Dxx"]) <= TOL_COV
+    De = gnp.scaled_distance_elementwise(th[1:], gnp.asarray(x[:k]), gnp.asarray(y[:k])).cpu().numpy()
+    assert relerr_norm(De, g["De"]) <= TOL_COV
+    Kii = gp.kernel.maternp_covariance(xd, xd, p, th).cpu().numpy()
+    assert relerr(Kii, g["Kii"]) <= TOL_COV
+    assert np.array_equal(Kii, Kii.T)
+    Kn = gp.kernel.maternp_covariance(xd, None, p, th).cpu().numpy()
+    assert relerr(Kn, g["Kii_none"]) <= TOL_COV
+    Kit = gp.kernel.maternp_covariance(xd, yd, p, th).cpu().numpy()
+    assert relerr(Kit, g["Kit"]) <= TOL_COV
+    assert relerr(gp.kernel.maternp_covariance(xd, None, p, th, True).cpu().numpy(), g["Kii_pw"]) <= TOL_COV
+    pw = gp.kernel.maternp_covariance(gnp.asarray(x[:k]), gnp.asarray(y[:k]), p, th, True).cpu().numpy()
+    assert relerr(pw, g["Kit_pw"]) <= TOL_COV
+    kh = gp.kernel.maternp_kernel(p, gnp.asarray(g["h"])).cpu().numpy()
+    ok = ~np.isnan(g["kh"])
+    assert np.array_equal(np.isnan(kh), np.isnan(g["kh"]))
+    assert relerr_norm(kh[ok], g["kh"][ok]) <= TOL_COV
+
+
+def test_covariance_empty_and_ragged(gp):
+    gnp = gp.num
+    x = gnp.asarray(np.random.default_rng(0).uniform(size=(65, 3)))
+    th = np.array([0.1, 0.2, -0.3, 0.4])
+    assert gp.kernel.maternp_covariance(x[:0], x[:0].clone(), 2, th).shape == (0, 0)
+    K = gp.kernel.maternp_covariance(x, x[:1].clone(), 2, th)
+    assert K.shape == (65, 1)
+    ref = onp.maternp_covariance(x.cpu().numpy(), x[:1].cpu().numpy(), 2, th)
+    assert relerr(K.cpu().numpy(), ref) <= TOL_COV
+
+
+def test_covariance_param_gradient(gp):
+    """vjp of the covariance op (dK regenerated per tile) against torch-CPU autograd of the oracle."""
+    from oracle import gp_torch as ot
+
+    rng = np.random.default_rng(5)
+    x = rng.uniform(size=(70, 3))
+    th = np.array([0.3, 0.1, -0.2, 0.5])
+    G = rng.standard_normal((70, 70))
+    for p in (0, 1, 2, 4):
+        tp = torch.tensor(th, requires_grad=True)
+        K = gp.kernel.maternp_covariance(gp.num.asarray(x), None, p, tp)
+        (K * gp.num.asarray(G)).sum().backward()
+        tr = torch.tensor(th, requires_grad=True)
+        Kr = ot.matern_cov_ii(torch.tensor(x), p, tr)
+        (Kr * torch.tensor(G)).sum().backward()
+        assert relerr_norm(tp.grad.numpy(), tr.grad.numpy()) <= 1e-10, p
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(128, 128, 128), (300, 200, 70), (257, 129, 515), (1, 5, 3), (640, 384, 1024)])
+def test_gemm_nt(gp, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A, B, C0 = rng.standard_normal((M, K)), rng.standard_normal((N, K)), rng.standard_normal((M, N))
+    ops = gp.ops
+    Ad, Bd, Cd = ops.padded(ops.to_device(A)), ops.padded(ops.to_device(B)), ops.padded(ops.to_device(C0))
+    ops.gemm_nt(Ad, Bd, C_out=Cd, alpha=-0.5, beta=2.0)
+    ref = -0.5 * A @ B.T + 2.0 * C0
+    assert relerr_norm(Cd.cpu().numpy(), ref) <= 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 6, 64, 127, 128, 129, 300, 700, 1500, 2500])
+def test_potrf_potri_trsm(gp, n):
+    rng = np.random.default_rng(n)
+    x = rng.uniform(size=(n, 3))
+    K = onp.maternp_covariance(x, x, 2, np.array([0.2, 1.0, 1.2, 0.8])) + 1e-6 * np.eye(n)
+    B = rng.standard_normal((5, n))
+    ops = gp.ops
+    fac = ops.potrf(ops.to_device(K), extra_rows=ops.to_device(B))
+    L = np.linalg.cholesky(K)
+    Lg = fac.lower().cpu().numpy()
+    assert relerr_norm(Lg, L) <= 1e-10
+    # extra rows ride along: B L^-T
+    from scipy.linalg import solve_triangular
+
+    W = solve_triangular(L, B.T, lower=True).T
+    assert relerr_norm(fac.A[n:, :n].cpu().numpy(), W) <= 1e-9
+    # mirrored upper tiles hold L^T
+    full = fac.A[:n, :n].cpu().numpy()
+    t = 128
+    for bi in range(0, n, t):
+        for bj in range(bi + t, n, t):
+            assert np.array_equal(full[bi:bi + t, bj:bj + t], Lg[bj:bj + t, bi:bi + t].T)
+    Kinv, Tlo, Tup = ops.potri(fac)
+    Ki = np.linalg.inv(K)
+    assert relerr_norm(np.tril(Kinv[:, :n].cpu().numpy()), np.tril(Ki)) <= 1e-7
+    Tl = np.tril(Tlo[:, :n].cpu().numpy())
+    assert relerr_norm(Tl, np.linalg.inv(L)) <= 1e-8
+    assert relerr_norm(np.triu(Tup[:, :n].cpu().numpy()), Tl.T) <= 1e-15
+    R = ops.padded(ops.to_device(B))
+    ops.trsm_rows(fac, R, trans=0)
+    assert relerr_norm(R.cpu().numpy(), W) <= 1e-9
+    ops.trsm_rows(fac, R, trans=1)
+    assert relerr_norm(R.cpu().numpy(), np.linalg.solve(K, B.T).T) <= 1e-7
+
+
+def test_potrf_not_positive_definite(gp):
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    with pytest.raises(torch.linalg.LinAlgError):
+        gp.num.cholesky(A)
+    fac = gp.ops.potrf(gp.ops.to_device(A), check_pd=False)
+    assert int(fac.info.item()) == 151
+
+
+def test_gnp_cholesky_family(gp):
+    rng = np.random.default_rng(3)
+    n = 333
+    x = rng.uniform(size=(n, 2))
+    K = onp.maternp_covariance(x, x, 1, np.array([0.0, 1.5, 1.5])) + 1e-8 * np.eye(n)
+    b = rng.standard_normal(n)
+    B = rng.standard_normal((n, 4))
+    gnp = gp.num
+    xs, L = gnp.cholesky_solve(K, b)
+    assert xs.shape == (n, 1)
+    assert relerr_norm(xs.cpu().numpy()[:, 0], np.linalg.solve(K, b)) <= 1e-8
+    assert relerr_norm(L.cpu().numpy(), np.linalg.cholesky(K)) <= 1e-10
+    X2, _ = gnp.cholesky_solve(K, B)
+    assert relerr_norm(X2.cpu().numpy(), np.linalg.solve(K, B)) <= 1e-8
+    assert relerr_norm(gnp.cholesky_inv(K).cpu().numpy(), np.linalg.inv(K)) <= 1e-7
+    y = gnp.solve_triangular(L, B, lower=True)
+    assert relerr_norm(y.cpu().numpy(), np.linalg.solve(np.linalg.cholesky(K), B)) <= 1e-9
+    c, low = gnp.cho_factor(K, lower=True)
+    assert relerr_norm(gnp.cho_solve((c, low), b).cpu().numpy(), np.linalg.solve(K, b)) <= 1e-8
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [c[0] for c in cases.LIK_CASES])
+def test_likelihoods_and_gradients(gp, golden_np, golden_t, case):
+    name, n, d, p, kind, noise, seed = next(c for c in cases.LIK_CASES if c[0] == case)
+    gn, gt = golden_np(case), golden_t(case)
+    x, z, th = gn["x"], gn["z"], gn["theta"]
+    m = _model(gp, kind, p, noise, th)
+    # values against the NumPy-backend reference
+    v = m.negative_log_likelihood_zero_mean(th, x, z)
+    assert relerr(v.item(), gn["nll_zero"]) <= TOL_LIK
+    assert relerr(m.norm_k_sqrd_with_zero_mean(x, z, th).item(), gn["norm_zero"]) <= TOL_LIK
+    # gradients against the torch-backend reference (autograd through every op)
+    tp = torch.tensor(th, requires_grad=True)
+    v = m.negative_log_likelihood_zero_mean(tp, x, z)
+    (g,) = torch.autograd.grad(v, tp)
+    assert g.device.type == "cpu" and g.shape == tp.shape
+    assert relerr_norm(g.numpy(), gt["nll_zero_grad"]) <= TOL_LIK
+    if "reml" in gn:
+        tp = torch.tensor(th, requires_grad=True)
+        v = m.negative_log_restricted_likelihood(tp, x, z)
+        assert v.ndim == 0 and v.grad_fn is not None
+        assert relerr(v.item(), gn["reml"]) <= TOL_LIK
+        (g,) = torch.autograd.grad(v, tp)
+        assert relerr_norm(g.numpy(), gt["reml_grad"]) <= TOL_LIK
+        assert relerr(m.norm_k_sqrd(x, z, th).item(), gn["norm_k"]) <= TOL_LIK
+    if "nll_param" in gn:
+        full = torch.tensor(np.concatenate((cases.MEANPARAM, th)), requires_grad=True)
+        v = m.negative_log_likelihood(full[:2], full[2:], x, z)
+        assert relerr(v.item(), gn["nll_param"]) <= TOL_LIK
+        (g,) = torch.autograd.grad(v, full)
+        assert relerr_norm(g.numpy(), gt["nll_param_grad"]) <= TOL_LIK
+
+
+def test_likelihood_not_pd_gives_inf(gp):
+    x = np.zeros((40, 2))  # identical points: K = sigma2 (11^T + 10 eps I) -> not PD in floating point
+    z = np.arange(40.0)
+    m = gp.core.Model(cases.mean_fn("const", gp.num),
+                      lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, 2, cp, pairwise))
+    th = torch.tensor([0.0, 0.0, 0.0], requires_grad=True)
+    v = m.negative_log_restricted_likelihood(th, x, z)
+    assert torch.isinf(v) and v > 0
+    val, grad = gp.num.value_and_grad(lambda t: m.negative_log_restricted_likelihood(t, x, z), th)
+    assert torch.isinf(val) and torch.all(grad == 0)
+
+
+def test_selection_criterion_lifecycle(gp, golden_np, golden_t):
+    """evaluate_pre_grad / gradient / evaluate_no_grad as SciPy drives them (torch_backend.py:547-604)."""
+    case = "lik_n500_d8_p2_const"
+    gn, gt = golden_np(case), golden_t(case)
+    m = _model(gp, "const", 2, False, gn["theta"])
+    crit = gp.num.DifferentiableSelectionCriterion(
+        lambda p_, x_, z_: m.negative_log_restricted_likelihood(p_, x_, z_), gn["x"], gn["z"])
+    f = crit.evaluate_pre_grad(gn["theta"])
+    assert isinstance(f, float) and relerr(f, gn["reml"]) <= TOL_LIK
+    g = crit.gradient(gn["theta"])
+    assert relerr_norm(np.asarray(g), gt["reml_grad"]) <= TOL_LIK
+    f2 = crit.evaluate_no_grad(gn["theta"])
+    assert relerr(float(f2), gn["reml"]) <= TOL_LIK
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [c[0] for c in cases.PRED_CASES])
+def test_predict_and_conditioning(gp, golden_np, case):
+    name, n, mt, d, p, kind, noise, seed = next(c for c in cases.PRED_CASES if c[0] == case)
+    g = golden_np(case)
+    x, z, xt, th = g["x"], g["z"], g["xt"], g["theta"]
+    m = _model(gp, kind, p, noise, th)
+    sigma2 = float(np.exp(th[0]))
+    mean, var, lam = m.predict(x, z, xt, return_lambdas=True)
+    assert isinstance(mean, np.ndarray) and mean.shape == (mt,) and lam.shape == (n, mt)
+    scale = max(float(np.max(np.abs(g["mean"]))), np.sqrt(sigma2))
+    assert np.max(np.abs(mean - g["mean"])) / scale <= TOL_PRED
+    assert np.max(np.abs(var - g["var"])) / sigma2 <= TOL_PRED
+    assert relerr_norm(lam.cpu().numpy(), g["lam"]) <= 1e-7
+    mean2, var2 = m.predict(x, z, xt)
+    assert np.array_equal(mean2, mean) or np.max(np.abs(mean2 - mean)) / scale <= 1e-12
+    # conditioning by kriging on the reference's unconditional paths
+    xi_ind, xt_ind = np.arange(n), n + np.arange(mt)
+    if kind == "param":
+        cond = m.conditional_sample_paths_parameterized_mean(g["ztsim"], x, xi_ind, z, xt, xt_ind, lam)
+    else:
+        cond = m.conditional_sample_paths(g["ztsim"], xi_ind, z, xt_ind, lam)
+    assert cond.shape == g["cond"].shape
+    assert np.max(np.abs(cond - g["cond"])) / max(1.0, float(np.max(np.abs(g["cond"])))) <= 1e-8
+    # the deterministic half of sample_paths: C @ normals with K(xt, xt) = C C^T
+    normals = np.random.default_rng(1).standard_normal((mt, 3))
+    zs = m.sample_paths_from_normals(xt, normals).cpu().numpy()
+    Ktt = g["Ktt"]
+    try:
+        C = np.linalg.cholesky(Ktt)
+        assert relerr_norm(zs, C @ normals) <= 1e-6
+    except np.linalg.LinAlgError:
+        pass
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [c[0] for c in cases.BATCH_CASES])
+def test_batched_criterion(gp, golden_np, case):
+    name, n, d, p, N, seed = next(c for c in cases.BATCH_CASES if c[0] == case)
+    g = golden_np(case)
+    m = _model(gp, "const", p, False, g["TH"][0])
+    crit = gp.batched.BatchedCriterion(m, g["x"], g["z"], p, kind="reml")
+    vals = crit(g["TH"])
+    assert vals.shape == (N,)
+    assert relerr(vals, g["vals"]) <= TOL_LIK
+    # small workspace -> several chunks, same answer
+    crit2 = gp.batched.BatchedCriterion(m, g["x"], g["z"], p, kind="reml", max_bytes=3 << 20)
+    assert np.array_equal(crit2(g["TH"]), vals)
+    lp = crit.logpdf_temp(g["TH"], 2.0, lower=g["TH"].min(0) + 1e-9, upper=g["TH"].max(0) + 1.0)
+    ref = onp.logpdf_temp(lambda t: vals[np.argmin(np.abs(g["TH"] - t).sum(1))], g["TH"], 2.0,
+                          g["TH"].min(0) + 1e-9, g["TH"].max(0) + 1.0)
+    assert np.array_equal(np.isinf(lp), np.isinf(ref))
+    assert relerr(lp[~np.isinf(lp)], ref[~np.isinf(ref)]) <= 1e-12
+
+
+def test_batched_matches_scalar_path_n512(gp):
+    """config-4 shape (n=512, d=4): batched values == the scalar fused path, particle by particle."""
+    x, z, _ = cases.data(512, 4, 77)
+    rng = np.random.default_rng(78)
+    th0 = cases.theta(4, 77)
+    TH = th0 + rng.uniform(-1.0, 1.0, size=(24, 5))
+    m = _model(gp, "const", 2, False, th0)
+    vals = gp.batched.BatchedCriterion(m, x, z, 2)(TH)
+    for i in range(0, 24, 5):
+        v = m.negative_log_restricted_likelihood(TH[i], x, z).item()
+        assert relerr(vals[i], v) <= 1e-12
+    ref = onp.negative_log_restricted_likelihood(
+        onp.OracleModel(cases.mean_fn("const", np), lambda a, b, cp, pw=False: onp.maternp_covariance(a, b, 2, cp, pw),
+                        None, th0, "linear_predictor"), TH[3], x, z)
+    assert relerr(vals[3], ref) <= TOL_LIK
+
+
+# ----------------------------------------------------------------------------------------------------
+def test_headline_size_properties(gp):
+    """n=8192, d=8 (BASELINE config 3): size-independent checks at full size.
+    (1) the closed form d value / d log sigma2 = 0.5 ((n-q) - quad) must match the contracted gradient;
+    (2) REML is invariant to adding a constant to z (the constant mean is profiled out);
+    (3) gradient against a central finite difference of the value along a random direction."""
+    x, z, th0 = cases.headline()
+    m = _model(gp, "const", 2, False, th0)
+    n = x.shape[0]
+    xd, zd = gp.num.asarray(x), gp.num.asarray(z)
+    tp = torch.tensor(th0, requires_grad=True)
+    v = m.negative_log_restricted_likelihood(tp, xd, zd)
+    (g,) = torch.autograd.grad(v, tp)
+    quad = m.norm_k_sqrd(xd, zd, th0).item()
+    assert abs(g[0].item() - 0.5 * ((n - 1) - quad)) <= 1e-8 * max(1.0, abs(g[0].item()))
+    v_shift = m.negative_log_restricted_likelihood(th0, xd, zd + 3.0).item()
+    assert abs(v_shift - v.item()) <= 1e-8 * abs(v.item())
+    rng = np.random.default_rng(2)
+    dirn = rng.standard_normal(th0.shape)
+    dirn /= np.linalg.norm(dirn)
+    h = 1e-4
+    fp = m.negative_log_restricted_likelihood(th0 + h * dirn, xd, zd).item()
+    fm = m.negative_log_restricted_likelihood(th0 - h * dirn, xd, zd).item()
+    fd = (fp - fm) / (2 * h)
+    assert abs(fd - float(g.numpy() @ dirn)) <= 1e-5 * max(1.0, abs(fd))
