@@ -56,7 +56,7 @@ static PotrfWs potrf_ws(int n, int nrows) {
     w.off_tup = align_up(tb, 256);
     w.off_w = w.off_tup + align_up(tb, 256);
     size_t wrows = (size_t)(nrows > w.NB ? nrows : w.NB);
-    w.total = w.off_w + align_up(wrows * w.NB * 8, 256);
+    w.total = w.off_w + align_up(2 * wrows * w.NB * 8, 256);  // two panel buffers (look-ahead)
     return w;
 }
 
@@ -249,6 +249,12 @@ int gpmp_transpose(const double* in_dev, long long ldi, double* out_dev, long lo
     return launch_transpose(in_dev, ldi, out_dev, ldo, rows, cols, (cudaStream_t)stream);
 }
 
+// development hook: phase timestamps (clock64) of the diagonal-tile kernel; not declared in the header
+int gpmp_debug_potf2(double* A_dev, long long lda, int nb, double* Tlo_dev, double* Tup_dev, int* info_dev,
+                     long long* clocks_dev, void* stream) {
+    return debug_potf2(A_dev, lda, nb, Tlo_dev, Tup_dev, info_dev, clocks_dev, (cudaStream_t)stream);
+}
+
 // ---- likelihoods ---------------------------------------------------------------------------------
 size_t gpmp_lik_workspace_bytes(int n, int q, int d, int want_grad) {
     if (n < 0 || q < 0 || q > GPMP_MAX_Q) return 0;
@@ -406,7 +412,7 @@ static BatchWs batch_ws(int n, int q) {
     w.nblk = ceil_div(n, w.NB);
     w.per_A = align_up((size_t)(w.nrows + 1) * w.lda * 8, 256);
     w.per_T = align_up((size_t)w.nblk * w.NB * w.NB * 8, 256);
-    w.per_W = align_up((size_t)(w.nrows > w.NB ? w.nrows : w.NB) * w.NB * 8, 256);
+    w.per_W = align_up((size_t)2 * (w.nrows > w.NB ? w.nrows : w.NB) * w.NB * 8, 256);
     w.per_mdev = align_up(sizeof(MaternDev), 256);
     w.per_particle = w.per_A + 2 * w.per_T + w.per_W + w.per_mdev;
     w.shared = 2 * align_up((size_t)(q > 0 ? q : 1) * w.lda * 8, 256) + 256 + 256;

@@ -5,19 +5,22 @@
 // and the whitening/conditioning GEMMs of predict.  Every product on the path is arranged so that
 // both operands are read with K contiguous (row-major "K-major" tiles), see DESIGN.md.
 //
-// Tiling: CTA 128x128, K chunk 16 (one 128-byte row per tile row), 4-stage cp.async pipeline,
-// 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 DMMA tiles, 128 accumulator registers/thread.
+// Two tile shapes of the same template:
+//   big    CTA 128x128, 16 warps as 4(M) x 4(N), warp tile 32x32 = 4x4 DMMA tiles (64 accumulator regs,
+//          4 warps per scheduler), 3 stages x 2 K-chunks of 16 (192 KB: one barrier per 32 k) -- the
+//          throughput shape (measured: same 31.5 TFLOP/s as 8 warps of 64x32 at large K, +8..25% at K<=512);
+//   small  CTA 64x64, 4 warps as 2 x 2, warp tile 32x32, 96 KB, 2 CTAs/SM -- for the latency-bound
+//          products inside a diagonal block, where a handful of 128-tiles would leave 140 SMs idle.
 // Shared tiles are dense 128-byte rows with the 16-byte chunk index XOR-swizzled by (row & 7) -- the
 // layout a TMA SWIZZLE_128B box produces.  Inside a K chunk the k index is permuted (lane kk owns
 // k = 4*kk + s at MMA step s) so each lane fetches its 4 steps with two conflict-free LDS.128.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gpmp {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
-constexpr int TILE_BYTES = BM * BK * 8;       // 16 KB
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;   // A tile + B tile
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES;  // 128 KB
+constexpr int BK = 16, STAGES = 3, SUBK = 2;
+constexpr int KGRAN = 128;  // granularity of the triangular K trimming (the tile grid of the operands)
 
 struct GemmKArgs {
     GemmDesc g;
@@ -45,25 +48,38 @@ __device__ __forceinline__ void decode_tile(const GemmKArgs& a, int t, int& ti, 
     }
 }
 
+// ROWS x 16 doubles -> swizzled smem tile; thread -> (row = tid/8 + (THREADS/8)*i, chunk = tid%8)
+template <int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile(uint32_t sdst, const double* __restrict__ src, long long ld,
                                           int row0, int nrows, int k, int k1, int tid) {
-    // 128 rows x 8 chunks of 16 B; thread -> (row = tid/8 + 32*i, chunk = tid%8)
-    int c = tid & 7;
-    int kk = k + 2 * c;
-    int rem = k1 - kk;
-    int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+    const int c = tid & 7;
+    const int kk = k + 2 * c;
+    const int rem = k1 - kk;
+    const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int r = (tid >> 3) + 32 * i;
-        int grow = row0 + r;
-        int bytes = (grow < nrows) ? nb : 0;
+    for (int i = 0; i < ROWS * 8 / THREADS; ++i) {
+        const int r = (tid >> 3) + (THREADS / 8) * i;
+        const int grow = row0 + r;
+        const int bytes = (grow < nrows) ? nb : 0;
         const double* p = bytes ? (src + (long long)grow * ld + kk) : src;
-        uint32_t d = sdst + r * 128 + ((c ^ (r & 7)) << 4);
+        const uint32_t d = sdst + r * 128 + ((c ^ (r & 7)) << 4);
         cp_async16(d, p, bytes);
     }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmKArgs a) {
+template <int WM, int WN, int MI, int NI>
+struct GemmCfg {
+    static constexpr int BM = WM * MI * 8, BN = WN * NI * 8, THREADS = WM * WN * 32;
+    static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
+    static constexpr int SUB_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = SUBK * SUB_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES;
+};
+
+template <int WM, int WN, int MI, int NI, int MINB>
+__global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKArgs a) {
+    using Cfg = GemmCfg<WM, WN, MI, NI>;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS;
     extern __shared__ __align__(1024) unsigned char smem[];
     const GemmDesc& g = a.g;
     int ti, tj;
@@ -74,72 +90,77 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmKArg
     const double* __restrict__ B = g.B + zb * g.strideB + yb * g.stride2B;
     double* __restrict__ C = g.C + zb * g.strideC + yb * g.stride2C;
 
-    // K trimming for triangular operands (tile granularity; the operand's zero part may hold
-    // anything -- e.g. the other triangle of a symmetrised store -- so trimming is also what makes
-    // the product correct, and callers keep triangular operands 128-aligned with the tile grid).
+    // K trimming for triangular operands (granularity KGRAN = the operands' 128-tile grid; the zero part
+    // of a triangular operand may hold anything outside its diagonal tiles -- e.g. the mirrored other
+    // triangle -- so trimming is also what makes the product correct).
     int k0 = 0, k1 = g.K;
-    if (g.krange == KR_FROM_ROW) k0 = min(m0, g.K);
-    else if (g.krange == KR_TO_ROW) k1 = min(g.K, m0 + BM);
-    else if (g.krange == KR_FROM_COL) k0 = min(n0, g.K);
-    else if (g.krange == KR_TO_COL) k1 = min(g.K, n0 + BN);
-    const int nk = k1 > k0 ? (k1 - k0 + BK - 1) / BK : 0;
+    if (g.krange == KR_FROM_ROW) k0 = min(m0 / KGRAN * KGRAN, g.K);
+    else if (g.krange == KR_TO_ROW) k1 = min(g.K, (m0 / KGRAN + 1) * KGRAN);
+    else if (g.krange == KR_FROM_COL) k0 = min(n0 / KGRAN * KGRAN, g.K);
+    else if (g.krange == KR_TO_COL) k1 = min(g.K, (n0 / KGRAN + 1) * KGRAN);
+    const int nk = k1 > k0 ? (k1 - k0 + SUBK * BK - 1) / (SUBK * BK) : 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;      // 2 x 4 warps
-    const int gq = lane >> 2, kk = lane & 3;       // fragment row/col group, k lane
+    const int wm = warp / WN, wn = warp % WN;
+    const int gq = lane >> 2, kk = lane & 3;  // fragment row/col group, k lane
     const uint32_t sbase = smem_u32(smem);
 
-    double acc[8][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto load_stage = [&](int slot, int chunk) {
+        const uint32_t st = sbase + slot * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int u = 0; u < SUBK; ++u) {
+            const int kc = k0 + (chunk * SUBK + u) * BK;
+            load_tile<BM, THREADS>(st + u * Cfg::SUB_BYTES, A, g.lda, m0, g.M, kc, k1, tid);
+            load_tile<BN, THREADS>(st + u * Cfg::SUB_BYTES + Cfg::A_BYTES, B, g.ldb, n0, g.N, kc, k1, tid);
+        }
+    };
 
     // prologue
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) {
-            uint32_t st = sbase + s * STAGE_BYTES;
-            load_tile(st, A, g.lda, m0, g.M, k0 + s * BK, k1, tid);
-            load_tile(st + TILE_BYTES, B, g.ldb, n0, g.N, k0 + s * BK, k1, tid);
-        }
+        if (s < nk) load_stage(s, s);
         cp_async_commit();
     }
 
     // per-thread swizzled fragment offsets (row & 7 == gq for every fragment row of this lane)
-    const uint32_t aoff = (wm * 64 + gq) * 128;
-    const uint32_t boff = TILE_BYTES + (wn * 32 + gq) * 128;
+    const uint32_t aoff = (wm * MI * 8 + gq) * 128;
+    const uint32_t boff = Cfg::A_BYTES + (wn * NI * 8 + gq) * 128;
     const uint32_t c0 = ((2 * kk) ^ gq) << 4, c1 = ((2 * kk + 1) ^ gq) << 4;
 
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
-            int nx = kt + STAGES - 1;
-            if (nx < nk) {
-                uint32_t st = sbase + (nx % STAGES) * STAGE_BYTES;
-                load_tile(st, A, g.lda, m0, g.M, k0 + nx * BK, k1, tid);
-                load_tile(st + TILE_BYTES, B, g.ldb, n0, g.N, k0 + nx * BK, k1, tid);
-            }
+            const int nx = kt + STAGES - 1;
+            if (nx < nk) load_stage(nx % STAGES, nx);
             cp_async_commit();
         }
-        const unsigned char* st = smem + (kt % STAGES) * STAGE_BYTES;
-        double af[8][4];
+#pragma unroll 1
+        for (int u = 0; u < SUBK; ++u) {
+            const unsigned char* st = smem + (kt % STAGES) * Cfg::STAGE_BYTES + u * Cfg::SUB_BYTES;
+            double af[MI][4];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) {
-            const double2 v0 = *reinterpret_cast<const double2*>(st + aoff + mi * 1024 + c0);
-            const double2 v1 = *reinterpret_cast<const double2*>(st + aoff + mi * 1024 + c1);
-            af[mi][0] = v0.x; af[mi][1] = v0.y; af[mi][2] = v1.x; af[mi][3] = v1.y;
-        }
+            for (int mi = 0; mi < MI; ++mi) {
+                const double2 v0 = *reinterpret_cast<const double2*>(st + aoff + mi * 1024 + c0);
+                const double2 v1 = *reinterpret_cast<const double2*>(st + aoff + mi * 1024 + c1);
+                af[mi][0] = v0.x; af[mi][1] = v0.y; af[mi][2] = v1.x; af[mi][3] = v1.y;
+            }
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const double2 w0 = *reinterpret_cast<const double2*>(st + boff + ni * 1024 + c0);
-            const double2 w1 = *reinterpret_cast<const double2*>(st + boff + ni * 1024 + c1);
-            const double bf[4] = {w0.x, w0.y, w1.x, w1.y};
+            for (int ni = 0; ni < NI; ++ni) {
+                const double2 w0 = *reinterpret_cast<const double2*>(st + boff + ni * 1024 + c0);
+                const double2 w1 = *reinterpret_cast<const double2*>(st + boff + ni * 1024 + c1);
+                const double bf[4] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
+                for (int s = 0; s < 4; ++s)
 #pragma unroll
-                for (int mi = 0; mi < 8; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][s], bf[s]);
+                    for (int mi = 0; mi < MI; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][s], bf[s]);
+            }
         }
     }
     cp_async_wait<0>();
@@ -148,12 +169,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmKArg
     const double alpha = g.alpha, beta = g.beta;
     double* __restrict__ Ct = g.Ct ? g.Ct + zb * g.strideCt + yb * g.stride2Ct : nullptr;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-        const int row = m0 + wm * 64 + mi * 8 + gq;
+    for (int mi = 0; mi < MI; ++mi) {
+        const int row = m0 + wm * MI * 8 + mi * 8 + gq;
         if (row >= g.M) continue;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int col = n0 + wn * 32 + ni * 8 + 2 * kk;
+        for (int ni = 0; ni < NI; ++ni) {
+            const int col = n0 + wn * NI * 8 + ni * 8 + 2 * kk;
             if (col >= g.N) continue;
             double* cp = C + (long long)row * g.ldc + col;
             double v0 = alpha * acc[mi][ni][0], v1 = alpha * acc[mi][ni][1];
@@ -177,6 +198,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const GemmKArg
     }
 }
 
+template <int WM, int WN, int MI, int NI, int MINB>
+static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
+    using Cfg = GemmCfg<WM, WN, MI, NI>;
+    static bool configured = false;
+    auto kern = gemm_nt_kernel<WM, WN, MI, NI, MINB>;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+            return GPMP_ERR_CUDA;
+        configured = true;
+    }
+    GemmKArgs a;
+    a.g = g;
+    a.tiles_m = ceil_div(g.M, Cfg::BM);
+    a.tiles_n = ceil_div(g.N, Cfg::BN);
+    long long ntiles;
+    if (g.lower) {
+        if (a.tiles_n > a.tiles_m) a.tiles_n = a.tiles_m;
+        ntiles = (long long)a.tiles_n * (a.tiles_n + 1) / 2 + (long long)(a.tiles_m - a.tiles_n) * a.tiles_n;
+    } else {
+        ntiles = (long long)a.tiles_m * a.tiles_n;
+    }
+    const double kavg = g.krange == KR_FULL ? (double)g.K : 0.5 * (double)g.K;
+    const double work = 2.0 * (double)ntiles * Cfg::BM * Cfg::BN * kavg * g.batch * g.batch2;
+    LaunchScope scope(KC_GEMM, work, stream);
+    dim3 grid((unsigned)ntiles, (unsigned)g.batch2, (unsigned)g.batch);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
 int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0 || g.batch2 <= 0) return GPMP_OK;
     // 16-byte cp.async / vector epilogue requirements
@@ -186,31 +237,20 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
         return GPMP_ERR_ALIGN;
     if ((g.strideA & 1) || (g.strideB & 1) || (g.strideC & 1)) return GPMP_ERR_ALIGN;
     if ((g.stride2A & 1) || (g.stride2B & 1) || (g.stride2C & 1)) return GPMP_ERR_ALIGN;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) !=
-            cudaSuccess)
-            return GPMP_ERR_CUDA;
-        configured = true;
+    // fewer 128-tiles than SMs: spread the work over 4x as many 64-tiles.  An in-place product (the
+    // single-column-tile panel solves) must keep one column tile per row block.
+    long long t128 = (long long)ceil_div(g.M, 128) * ceil_div(g.N, 128);
+    if (g.lower) t128 = t128 / 2 + ceil_div(g.N, 128);
+    t128 *= (long long)g.batch * g.batch2;
+    const bool in_place = (g.A == g.C || g.B == g.C);
+    if (t128 < 100 && !(in_place && g.N > 64)) return launch_cfg<2, 2, 4, 4, 2>(g, stream);
+    static int big_cfg = -1;
+    if (big_cfg < 0) {
+        const char* e = getenv("GPMP_GEMM_CFG");
+        big_cfg = e ? atoi(e) : 1;
     }
-    GemmKArgs a;
-    a.g = g;
-    a.tiles_m = ceil_div(g.M, BM);
-    a.tiles_n = ceil_div(g.N, BN);
-    long long ntiles;
-    if (g.lower) {
-        if (a.tiles_n > a.tiles_m) a.tiles_n = a.tiles_m;
-        ntiles = (long long)a.tiles_n * (a.tiles_n + 1) / 2 + (long long)(a.tiles_m - a.tiles_n) * a.tiles_n;
-    } else {
-        ntiles = (long long)a.tiles_m * a.tiles_n;
-    }
-    double kavg = g.krange == KR_FULL ? (double)g.K : 0.5 * (double)g.K;
-    double work = 2.0 * (double)ntiles * BM * BN * kavg * g.batch * g.batch2;
-    LaunchScope scope(KC_GEMM, work, stream);
-    dim3 grid((unsigned)ntiles, (unsigned)g.batch2, (unsigned)g.batch);
-    gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(a);
-    GPMP_CHECK_LAUNCH();
-    return GPMP_OK;
+    if (big_cfg == 0) return launch_cfg<2, 4, 8, 4, 1>(g, stream);  // 8 warps of 64x32 (development switch)
+    return launch_cfg<4, 4, 4, 4, 1>(g, stream);
 }
 
 }  // namespace gpmp

@@ -40,6 +40,9 @@ int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,
                    double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream);
 
+int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int* info, long long* dbg,
+                cudaStream_t stream);
+
 // ---- lik.cu
 struct LoadRowsArgs {
     const double* P; const double* z; int n, q;

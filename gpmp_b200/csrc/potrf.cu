@@ -14,15 +14,16 @@
 // SYRK), its inverse is assembled by block doubling (inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1,C^-1]]),
 // the panel below is solved with ONE GEMM against that inverse and the trailing matrix gets ONE
 // K=NB SYRK.  Extra rows n..nrows-1 ride along in every panel solve (they leave as B L^-T).
+#include <vector>
 #include "internal.cuh"
 
 namespace gpmp {
 
 constexpr int PT = 128;          // base tile
-constexpr int PLD = 129;         // smem leading dimension of the tile
-constexpr int XLD = 65;          // smem leading dimension of the doubling scratch
+constexpr int PLD = 130;         // smem leading dimension of the tile (even: rows stay 16-byte aligned)
+constexpr int XLD = 66;          // smem leading dimension of the scratch
 constexpr int POTF2_THREADS = 512;
-constexpr int POTF2_SMEM = (PT * PLD + 64 * XLD + PT) * 8;
+constexpr int POTF2_SMEM = (PT * PLD + 96 * XLD + PT) * 8;
 
 struct Potf2Args {
     double* A; long long lda; long long strideA;      // tile origin (diagonal position), in/out
@@ -30,127 +31,197 @@ struct Potf2Args {
     int nb;            // live size of the tile (<= 128); the rest is padded with identity
     int* info; long long strideInfo;
     int row0;          // global index of the tile's first row (for info)
+    long long* dbg;    // optional: clock64() at the phase boundaries (development only)
 };
+#define POTF2_STAMP(i)                                              \
+    do {                                                            \
+        if (a.dbg && threadIdx.x == 0) a.dbg[i] = clock64();        \
+    } while (0)
 
 // ---- tiny warp-level DMMA GEMM over shared memory -------------------------------------------
-// For every 8x8 output tile (i8, j8) accepted by `pick`, computes sum_k a(i,k) * b(j,k) over
-// k in [0,K) (K multiple of 4) and hands the two accumulators of each lane to `out(i, j, c0, c1)`
-// (element (i, j) and (i, j+1)).
-template <class FA, class FB, class FP, class FO>
-__device__ __forceinline__ void smem_mma(int M8, int N8, int K, FA a, FB b, FP pick, FO out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// For every 8x8 output tile (i8, j8) accepted by `pick` (tiles dealt round-robin to warps wid, wid+nw, ...),
+// computes sum_k a(i,k) * b(j,k) over k in [0,K) and hands the two accumulators of each lane to
+// `out(i, j, c0, c1)` (elements (i, j) and (i, j+1)).  K is a template parameter: all fragments of a tile
+// are fetched before the first DMMA so the shared-memory latency is paid once per tile.
+template <int K, class FA, class FB, class FP, class FO>
+__device__ __forceinline__ void smem_mma(int M8, int N8, int wid, int nw, FA a, FB b, FP pick, FO out) {
+    const int lane = threadIdx.x & 31;
     const int gq = lane >> 2, kk = lane & 3;
-    for (int t = warp; t < M8 * N8; t += nw) {
+    for (int t = wid; t < M8 * N8; t += nw) {
         const int i8 = t / N8, j8 = t - i8 * N8;
         if (!pick(i8, j8)) continue;
-        double c0 = 0.0, c1 = 0.0;
         const int i = i8 * 8 + gq, j = j8 * 8 + gq;
-        for (int k = 0; k < K; k += 4) dmma884(c0, c1, a(i, k + kk), b(j, k + kk));
-        out(i, j8 * 8 + 2 * kk, c0, c1);
+        double av[K / 4], bv[K / 4];
+#pragma unroll
+        for (int s = 0; s < K / 4; ++s) {
+            av[s] = a(i, 4 * s + kk);
+            bv[s] = b(j, 4 * s + kk);
+        }
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < K / 4; s += 2) {  // two independent accumulator pairs hide the DMMA latency
+            dmma884(c0, c1, av[s], bv[s]);
+            if (s + 1 < K / 4) dmma884(d0, d1, av[s + 1], bv[s + 1]);
+        }
+        out(i, j8 * 8 + 2 * kk, c0 + d0, c1 + d1);
     }
 }
 
+// 1/sqrt(a) in double from the single-precision MUFU seed and two Newton steps (the library rsqrt()
+// is a long software sequence; this one sits on the per-column critical chain of the tile factor).
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    if (!(a > 1e-30 && a < 1e30)) return rsqrt(a);
+    double y = (double)rsqrtf((float)a);
+    const double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);  // 22 -> 44 bits
+    y = y * fma(-h * y, y, 1.5);  // -> full double
+    return y;
+}
+
 // Factor one 128x128 diagonal tile (lower) and invert the factor.  One CTA per tile.
-// smem S: lower = L, strict upper = T^T (T_ij stored at S[j][i]), tdiag = diag(T).
+//
+// The tile lives in shared memory for the whole kernel:  S lower = L,  S strict upper = T^T
+// (T_ij kept at S[j][i]),  rinv = 1 / diag(L) = diag(T).  Everything is hierarchical 8 -> 32 -> 128 so that
+// the only serial code is the pivot chain of an 8x8 block in the registers of one lane:
+//   factor   4 panels of 32 columns, right-looking.  Inside a panel warp 0 walks four 8-column sub-panels:
+//            one lane factors the 8x8 diagonal block, the lanes below solve their row against it, the warp
+//            applies the rank-8 update with DMMA.  Then every thread below the panel solves one row by
+//            forward substitution and all warps apply the rank-32 update with DMMA.
+//   invert   8x8 diagonal blocks in registers, then block doubling T_ba = -T_bb (L_ba T_aa) with DMMA:
+//            8 -> 16 -> 32 inside one warp per 32-block, 32 -> 64 -> 128 with all warps.
 __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args a) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
     double* X = sm + PT * PLD;
-    double* tdiag = X + 64 * XLD;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* rinv = X + 96 * XLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = POTF2_THREADS / 32;
     const long long zb = blockIdx.x;
     double* __restrict__ A = a.A + zb * a.strideA;
     const int nb = a.nb;
+    POTF2_STAMP(0);
 
-    // load the lower triangle, identity padding outside the live block
-    for (int e = tid; e < PT * PT; e += POTF2_THREADS) {
-        const int r = e >> 7, c = e & 127;
-        double v = 0.0;
-        if (r < nb && c <= r) v = A[(long long)r * a.lda + c];
-        else if (r == c) v = 1.0;
-        S[r * PLD + c] = v;
+    // load the lower triangle with 16-byte async copies (all in flight at once), then patch the strict
+    // upper part to zero and pad the dead rows/columns with identity
+    {
+        const uint32_t sb = smem_u32(S);
+        for (int e = tid; e < PT * (PT / 2); e += POTF2_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;  // chunk of two columns
+            if (c > r) continue;
+            int bytes = 0;
+            if (r < nb) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+            const double* src = bytes ? A + (long long)r * a.lda + c : A;
+            cp_async16(sb + (uint32_t)(r * PLD + c) * 8u, src, bytes);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int e = tid; e < PT * (PT / 2); e += POTF2_THREADS) {
+            // strict upper part, two columns at a time (the chunk holding the diagonal keeps its first entry)
+            const int r = e >> 6, c = (e & 63) * 2;
+            if (c + 1 <= r) continue;
+            if (c > r) S[r * PLD + c] = 0.0;
+            S[r * PLD + c + 1] = 0.0;
+        }
+        if (tid >= nb && tid < PT) S[tid * PLD + tid] = 1.0;
     }
     __syncthreads();
 
-    int bad = 0;  // 1-based local index of the first non-positive pivot (warp 0 only)
+    POTF2_STAMP(1);
+    int bad = 0;  // 1-based local index of the first non-positive pivot (warp 0, lane 0 only)
     for (int jb = 0; jb < 4; ++jb) {
         const int c0 = jb * 32;
+        POTF2_STAMP(2 + 3 * jb);
         if (warp == 0) {
-            // (a) left-looking Cholesky of the 32x32 diagonal block, lane = row
             double* D = S + c0 * PLD + c0;
-            for (int j = 0; j < 32; ++j) {
-                double s0 = 0.0, s1 = 0.0;
-                if (lane >= j) {
-                    int k = 0;
-                    for (; k + 1 < j; k += 2) {
-                        s0 = fma(D[lane * PLD + k], D[j * PLD + k], s0);
-                        s1 = fma(D[lane * PLD + k + 1], D[j * PLD + k + 1], s1);
+            for (int sb = 0; sb < 4; ++sb) {
+                const int o = sb * 8;
+                if (lane == 0) {
+                    // 8x8 diagonal block: the pivot chain, entirely in registers
+                    double m[8][8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) m[i][j] = D[(o + i) * PLD + o + j];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double piv = m[j][j];
+                        if (!(piv > 0.0) && bad == 0) bad = c0 + o + j + 1;
+                        const double ri = fast_rsqrt(piv);
+                        m[j][j] = piv * ri;
+                        rinv[c0 + o + j] = ri;
+#pragma unroll
+                        for (int i = j + 1; i < 8; ++i) m[i][j] *= ri;
+#pragma unroll
+                        for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+                            for (int k = j + 1; k <= i; ++k) m[i][k] = fma(-m[i][j], m[k][j], m[i][k]);
                     }
-                    if (k < j) s0 = fma(D[lane * PLD + k], D[j * PLD + k], s0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) D[(o + i) * PLD + o + j] = m[i][j];
                 }
-                const double v = (lane >= j ? D[lane * PLD + j] : 0.0) - (s0 + s1);
-                const double piv = __shfl_sync(0xffffffffu, v, j);
-                if (!(piv > 0.0) && bad == 0) bad = c0 + j + 1;
-                const double dj = sqrt(piv);
-                if (lane == j) D[j * PLD + j] = dj;
-                else if (lane > j) D[lane * PLD + j] = v / dj;
                 __syncwarp();
-            }
-            // (b) invert it: lane = column j of T; T_ij kept at the transposed (upper) position
-            {
-                const int j = lane;
-                const double tjj = 1.0 / D[j * PLD + j];
-                tdiag[c0 + j] = tjj;
-                for (int i = j + 1; i < 32; ++i) {
-                    double s0 = D[i * PLD + j] * tjj, s1 = 0.0;
-                    int k = j + 1;
-                    for (; k + 1 < i; k += 2) {
-                        s0 = fma(D[i * PLD + k], D[j * PLD + k], s0);
-                        s1 = fma(D[i * PLD + k + 1], D[j * PLD + k + 1], s1);
+                if (lane >= o + 8) {
+                    // rows of the block below the 8x8: x = p L8^-T, one row per lane
+                    double xr[8];
+                    double* myrow = D + lane * PLD;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) xr[t] = myrow[o + t];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        xr[t] *= rinv[c0 + o + t];
+#pragma unroll
+                        for (int u = t + 1; u < 8; ++u) xr[u] = fma(-xr[t], D[(o + u) * PLD + o + t], xr[u]);
                     }
-                    if (k < i) s0 = fma(D[i * PLD + k], D[j * PLD + k], s0);
-                    D[j * PLD + i] = -(s0 + s1) / D[i * PLD + i];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) myrow[o + t] = xr[t];
                 }
+                __syncwarp();
+                if (o < 24) {
+                    // rank-8 update of the rest of the block (lower 8x8 tiles) on the tensor pipe
+                    const double* Px = D + (o + 8) * PLD + o;
+                    double* Cx = D + (o + 8) * PLD + o + 8;
+                    const int m8 = (24 - o) / 8;
+                    smem_mma<8>(
+                        m8, m8, 0, 1, [&](int i, int k) { return Px[i * PLD + k]; },
+                        [&](int j, int k) { return Px[j * PLD + k]; }, [&](int i8, int j8) { return j8 <= i8; },
+                        [&](int i, int j, double c0v, double c1v) {
+                            if (j <= i) Cx[i * PLD + j] -= c0v;
+                            if (j + 1 <= i) Cx[i * PLD + j + 1] -= c1v;
+                        });
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
+        POTF2_STAMP(3 + 3 * jb);
         const int rb = c0 + 32;       // first row below the diagonal block
         const int mrows = PT - rb;    // rows below
         if (mrows > 0) {
-            // (c) X = S[rb.., c0..c0+32) * Td^T   (Td = inverse of the diagonal block), into scratch
-            //     thread -> (row, group of 8 columns)
-            for (int e = tid; e < mrows * 4; e += POTF2_THREADS) {
-                const int r = e % mrows, cg = e / mrows;
-                const double* src = S + (rb + r) * PLD + c0;
-                double o[8];
+            // rows below: x = p Ld^-T by forward substitution, one thread per row (Ld broadcast from smem)
+            if (tid < mrows) {
+                double* prow = S + (rb + tid) * PLD + c0;
+                const double* D = S + c0 * PLD + c0;
+                double x[32];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) o[u] = 0.0;
-                for (int k = 0; k < 8 * cg + 8; ++k) {
-                    const double v = src[k];
+                for (int k = 0; k < 32; ++k) x[k] = prow[k];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = 8 * cg + u;
-                        // T[j][k] : k<j at S[c0+k][c0+j], k==j tdiag, k>j zero
-                        const double t = k < j ? S[(c0 + k) * PLD + c0 + j] : (k == j ? tdiag[c0 + j] : 0.0);
-                        o[u] = fma(v, t, o[u]);
-                    }
+                for (int k = 0; k < 32; ++k) {
+                    x[k] *= rinv[c0 + k];
+#pragma unroll
+                    for (int j = k + 1; j < 32; ++j) x[j] = fma(-x[k], D[j * PLD + k], x[j]);
                 }
-                // scratch is 64 x XLD: rows r (< 96) do not fit -> use two halves of 48 rows x 32
-                double* dst = X + (r % 48) * XLD + (r / 48) * 32 + 0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) dst[8 * cg + u] = o[u];
+                for (int k = 0; k < 32; ++k) prow[k] = x[k];
             }
             __syncthreads();
-            for (int e = tid; e < mrows * 32; e += POTF2_THREADS) {
-                const int r = e >> 5, c = e & 31;
-                S[(rb + r) * PLD + c0 + c] = X[(r % 48) * XLD + (r / 48) * 32 + c];
-            }
-            __syncthreads();
-            // (d) trailing update of the lower 8x8 tiles: S[rb.., rb..] -= P P^T, P = S[rb.., c0..c0+32)
+            POTF2_STAMP(4 + 3 * jb);
+            // trailing update of the lower 8x8 tiles: S[rb.., rb..] -= P P^T, P = S[rb.., c0..c0+32)
             const double* P = S + rb * PLD + c0;
             double* C = S + rb * PLD + rb;
-            smem_mma(
-                mrows / 8, mrows / 8, 32, [&](int i, int k) { return P[i * PLD + k]; },
+            smem_mma<32>(
+                mrows / 8, mrows / 8, warp, nwarps, [&](int i, int k) { return P[i * PLD + k]; },
                 [&](int j, int k) { return P[j * PLD + k]; }, [&](int i8, int j8) { return j8 <= i8; },
                 [&](int i, int j, double c0v, double c1v) {
                     // diagonal 8x8 tiles: touch the lower part only (the upper part is reserved for T^T)
@@ -165,53 +236,162 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
         atomicCAS(ip, 0, a.row0 + bad);
     }
 
-    // ---- inverse by doubling: 32 -> 64 -> 128 ------------------------------------------------
-    // T(i,k) for the already inverted diagonal blocks
+    POTF2_STAMP(14);
+    // T(i,k) for the already inverted diagonal blocks (tile coordinates)
     auto Tget = [&](int i, int k) -> double {
-        return i > k ? S[k * PLD + i] : (i == k ? tdiag[i] : 0.0);
+        return i > k ? S[k * PLD + i] : (i == k ? rinv[i] : 0.0);
     };
-    for (int s = 32; s < PT; s *= 2) {
-        for (int pr = 0; pr < PT / (2 * s); ++pr) {
-            const int a0 = 2 * pr * s, b0 = a0 + s;
-            // X (s x s) = L_ba * T_aa
-            smem_mma(
-                s / 8, s / 8, s, [&](int i, int k) { return S[(b0 + i) * PLD + a0 + k]; },
+    // ---- inverse of the four 32x32 diagonal blocks, one warp each: 8x8 in registers, then 8 -> 16 -> 32 ---
+    if (warp < 4) {
+        const int c0 = warp * 32;
+        double* Xw = X + warp * 16 * XLD;  // per-warp scratch (16 x 16)
+        if (lane < 4) {
+            const int q0 = c0 + 8 * lane;
+            double l[8][8], t[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j) l[i][j] = S[(q0 + i) * PLD + q0 + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                t[j][j] = rinv[q0 + j];
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = j; k < i; ++k) acc = fma(l[i][k], t[k][j], acc);
+                    t[i][j] = -acc * rinv[q0 + i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j) S[(q0 + j) * PLD + q0 + i] = t[i][j];
+        }
+        __syncwarp();
+        // s = 8: pairs (0,1) and (2,3) of 8-blocks
+        for (int pr = 0; pr < 2; ++pr) {
+            const int a0 = c0 + 16 * pr, b0 = a0 + 8;
+            smem_mma<8>(
+                1, 1, 0, 1, [&](int i, int k) { return S[(b0 + i) * PLD + a0 + k]; },
                 [&](int j, int k) { return Tget(a0 + k, a0 + j); }, [&](int, int) { return true; },
                 [&](int i, int j, double c0v, double c1v) {
-                    X[i * XLD + j] = c0v;
-                    X[i * XLD + j + 1] = c1v;
+                    Xw[(8 * pr + i) * XLD + j] = c0v;
+                    Xw[(8 * pr + i) * XLD + j + 1] = c1v;
                 });
-            __syncthreads();
-            // T_ba = -T_bb * X, stored transposed in the upper part: S[a0 + j][b0 + i]
-            smem_mma(
-                s / 8, s / 8, s, [&](int i, int k) { return Tget(b0 + i, b0 + k); },
-                [&](int j, int k) { return X[k * XLD + j]; }, [&](int, int) { return true; },
+        }
+        __syncwarp();
+        for (int pr = 0; pr < 2; ++pr) {
+            const int a0 = c0 + 16 * pr, b0 = a0 + 8;
+            smem_mma<8>(
+                1, 1, 0, 1, [&](int i, int k) { return Tget(b0 + i, b0 + k); },
+                [&](int j, int k) { return Xw[(8 * pr + k) * XLD + j]; }, [&](int, int) { return true; },
                 [&](int i, int j, double c0v, double c1v) {
                     S[(a0 + j) * PLD + b0 + i] = -c0v;
                     S[(a0 + j + 1) * PLD + b0 + i] = -c1v;
                 });
-            __syncthreads();
+        }
+        __syncwarp();
+        // s = 16
+        {
+            const int a0 = c0, b0 = c0 + 16;
+            smem_mma<16>(
+                2, 2, 0, 1, [&](int i, int k) { return S[(b0 + i) * PLD + a0 + k]; },
+                [&](int j, int k) { return Tget(a0 + k, a0 + j); }, [&](int, int) { return true; },
+                [&](int i, int j, double c0v, double c1v) {
+                    Xw[i * XLD + j] = c0v;
+                    Xw[i * XLD + j + 1] = c1v;
+                });
+            __syncwarp();
+            smem_mma<16>(
+                2, 2, 0, 1, [&](int i, int k) { return Tget(b0 + i, b0 + k); },
+                [&](int j, int k) { return Xw[k * XLD + j]; }, [&](int, int) { return true; },
+                [&](int i, int j, double c0v, double c1v) {
+                    S[(a0 + j) * PLD + b0 + i] = -c0v;
+                    S[(a0 + j + 1) * PLD + b0 + i] = -c1v;
+                });
         }
     }
+    __syncthreads();
+    POTF2_STAMP(15);
+
+    // ---- inverse by doubling: 32 -> 64 (two pairs) -> 128, all warps -----------------------------------
+    for (int pr = 0; pr < 2; ++pr) {
+        const int a0 = 64 * pr, b0 = a0 + 32;
+        double* Xp = X + pr * 32 * XLD;
+        smem_mma<32>(
+            4, 4, warp, nwarps, [&](int i, int k) { return S[(b0 + i) * PLD + a0 + k]; },
+            [&](int j, int k) { return Tget(a0 + k, a0 + j); }, [&](int, int) { return true; },
+            [&](int i, int j, double c0v, double c1v) {
+                Xp[i * XLD + j] = c0v;
+                Xp[i * XLD + j + 1] = c1v;
+            });
+    }
+    __syncthreads();
+    for (int pr = 0; pr < 2; ++pr) {
+        const int a0 = 64 * pr, b0 = a0 + 32;
+        const double* Xp = X + pr * 32 * XLD;
+        smem_mma<32>(
+            4, 4, warp, nwarps, [&](int i, int k) { return Tget(b0 + i, b0 + k); },
+            [&](int j, int k) { return Xp[k * XLD + j]; }, [&](int, int) { return true; },
+            [&](int i, int j, double c0v, double c1v) {
+                S[(a0 + j) * PLD + b0 + i] = -c0v;
+                S[(a0 + j + 1) * PLD + b0 + i] = -c1v;
+            });
+    }
+    __syncthreads();
+    POTF2_STAMP(16);
+    smem_mma<64>(
+        8, 8, warp, nwarps, [&](int i, int k) { return S[(64 + i) * PLD + k]; },
+        [&](int j, int k) { return Tget(k, j); }, [&](int, int) { return true; },
+        [&](int i, int j, double c0v, double c1v) {
+            X[i * XLD + j] = c0v;
+            X[i * XLD + j + 1] = c1v;
+        });
+    __syncthreads();
+    smem_mma<64>(
+        8, 8, warp, nwarps, [&](int i, int k) { return Tget(64 + i, 64 + k); },
+        [&](int j, int k) { return X[k * XLD + j]; }, [&](int, int) { return true; },
+        [&](int i, int j, double c0v, double c1v) {
+            S[j * PLD + 64 + i] = -c0v;
+            S[(j + 1) * PLD + 64 + i] = -c1v;
+        });
+    __syncthreads();
+    POTF2_STAMP(17);
 
     // ---- write back: L (lower, zero upper) into A; T into Tlo (lower) / Tup (upper) -------------
-    for (int e = tid; e < PT * PT; e += POTF2_THREADS) {
-        const int r = e >> 7, c = e & 127;
-        if (r < nb && c < nb) A[(long long)r * a.lda + c] = c <= r ? S[r * PLD + c] : 0.0;
-    }
-    if (a.Tlo) {
-        double* __restrict__ Tlo = a.Tlo + zb * a.strideT;
-        double* __restrict__ Tup = a.Tup + zb * a.strideT;
-        for (int e = tid; e < PT * PT; e += POTF2_THREADS) {
-            const int r = e >> 7, c = e & 127;
-            if (r < nb && c < nb) {
-                const double t = r > c ? S[c * PLD + r] : (r == c ? tdiag[r] : 0.0);  // T[r][c]
-                const double tt = c > r ? S[r * PLD + c] : (r == c ? tdiag[r] : 0.0); // T^T[r][c] = T[c][r]
-                Tlo[(long long)r * a.ldt + c] = t;
-                Tup[(long long)r * a.ldt + c] = tt;
+    // two columns per thread and step: 16-byte stores when the row is even-aligned and fully live
+    const bool vec = ((a.lda & 1) == 0) && ((a.ldt & 1) == 0);
+    for (int e = tid; e < PT * (PT / 2); e += POTF2_THREADS) {
+        const int r = e >> 6, c = (e & 63) * 2;
+        if (r >= nb || c >= nb) continue;
+        const double l0 = c <= r ? S[r * PLD + c] : 0.0;
+        const double l1 = c + 1 <= r ? S[r * PLD + c + 1] : 0.0;
+        double* dst = A + (long long)r * a.lda + c;
+        if (vec && c + 1 < nb) *reinterpret_cast<double2*>(dst) = make_double2(l0, l1);
+        else {
+            dst[0] = l0;
+            if (c + 1 < nb) dst[1] = l1;
+        }
+        if (a.Tlo) {
+            double* __restrict__ Tlo = a.Tlo + zb * a.strideT + (long long)r * a.ldt + c;
+            double* __restrict__ Tup = a.Tup + zb * a.strideT + (long long)r * a.ldt + c;
+            // T[r][c] lives at S[c][r] (r > c); T^T[r][c] = T[c][r] lives at S[r][c] (c > r)
+            const double t0 = r > c ? S[c * PLD + r] : (r == c ? rinv[r] : 0.0);
+            const double t1 = r > c + 1 ? S[(c + 1) * PLD + r] : (r == c + 1 ? rinv[r] : 0.0);
+            const double u0 = c > r ? S[r * PLD + c] : (r == c ? rinv[r] : 0.0);
+            const double u1 = c + 1 > r ? S[r * PLD + c + 1] : (r == c + 1 ? rinv[r] : 0.0);
+            if (vec && c + 1 < nb) {
+                *reinterpret_cast<double2*>(Tlo) = make_double2(t0, t1);
+                *reinterpret_cast<double2*>(Tup) = make_double2(u0, u1);
+            } else {
+                Tlo[0] = t0; Tup[0] = u0;
+                if (c + 1 < nb) { Tlo[1] = t1; Tup[1] = u1; }
             }
         }
     }
+    __syncthreads();
+    POTF2_STAMP(18);
 }
 
 static int launch_potf2(const Potf2Args& a, int batch, cudaStream_t stream) {
@@ -226,6 +406,15 @@ static int launch_potf2(const Potf2Args& a, int batch, cudaStream_t stream) {
     potf2_kernel<<<batch, POTF2_THREADS, POTF2_SMEM, stream>>>(a);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
+}
+
+// development hook (not part of the C-ABI header): one tile with phase timestamps
+int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int* info, long long* dbg,
+                cudaStream_t stream) {
+    Potf2Args pa;
+    pa.A = A; pa.lda = lda; pa.strideA = 0; pa.Tlo = Tlo; pa.Tup = Tup; pa.ldt = PT; pa.strideT = 0; pa.nb = nb;
+    pa.info = info; pa.strideInfo = 0; pa.row0 = 0; pa.dbg = dbg;
+    return launch_potf2(pa, 1, stream);
 }
 
 // ---- panel copy-back: W (rows x nb, ld ldw) -> A panel (lower) and its mirror in the upper tiles --
@@ -311,110 +500,208 @@ static int doubling_level(const double* L, long long ldl, long long strideL, dou
     return GPMP_OK;
 }
 
-// Core factorisation (optionally batched over blockIdx.z with element strides).
-//   A      (nrows x lda)            in: lower of K (+ extra rows); out: L both-ways (+ whitened rows)
-//   Tlo/Tup compact diagonal-block inverses: nblk blocks of NB x NB (ld NB), block b at b*NB*NB
-//   W      panel scratch (nrows x NB, ld NB), needed when NB > 128
-int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
-               long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream) {
-    if (n <= 0) return GPMP_OK;
+// ---- pieces of one outer step (all optionally batched over blockIdx.z with element strides) ------
+struct PotrfCtx {
+    double* A; long long lda, strideA;
+    int n, nrows, NB;
+    double* Tlo; double* Tup; long long strideT;
+    int* info; long long strideInfo;
+    int batch;
+};
+
+// Column group [k0, k0+gw) (gw <= NB): 128-wide steps, each = tile factor+inverse, solve of ALL rows below
+// the tile against the tile inverse (out of place into the group panel buffer, 64-tiles when the product
+// is small), copy-back + mirror, and the K=128 update of the columns that remain inside the group.  When
+// the loop ends the buffer holds the complete solved panel of the group: W[(r - k0)][j] = L[r][k0 + j] for
+// every row r below the tile of column j (rows n..nrows-1 included), so no NB-wide triangular solve and no
+// NB-wide block inverse sit on the critical path (the inverses are doubled up after the factorisation).
+static int group_panel(const PotrfCtx& c, int k0, double* Wg, long long strideW, cudaStream_t stream) {
+    const int NB = c.NB, gw = min(NB, c.n - k0);
+    const long long lda = c.lda;
+    double* Tlo_k = c.Tlo + (long long)(k0 / NB) * NB * NB;
+    double* Tup_k = c.Tup + (long long)(k0 / NB) * NB * NB;
     int rc;
-    for (int k = 0; k < n; k += NB) {
-        const int nbk = min(NB, n - k);
-        double* Akk = A + (long long)k * (lda + 1);
-        double* Tlo_k = Tlo + (long long)(k / NB) * NB * NB;
-        double* Tup_k = Tup + (long long)(k / NB) * NB * NB;
-        // ---- diagonal block: 128-wide sub-steps
-        for (int j0 = 0; j0 < nbk; j0 += PT) {
-            const int jb = min(PT, nbk - j0);
-            Potf2Args pa;
-            pa.A = Akk + (long long)j0 * (lda + 1); pa.lda = lda; pa.strideA = strideA;
-            pa.Tlo = Tlo_k + (long long)j0 * (NB + 1); pa.Tup = Tup_k + (long long)j0 * (NB + 1);
-            pa.ldt = NB; pa.strideT = strideT; pa.nb = jb; pa.info = info; pa.strideInfo = strideInfo;
-            pa.row0 = k + j0;
-            rc = launch_potf2(pa, batch, stream);
-            if (rc) return rc;
-            const int m = nbk - (j0 + jb);
-            if (m > 0) {
-                // in-place TRSM of the rows below inside the diagonal block (single column tile)
-                GemmDesc g = gemm_desc();
-                g.A = Akk + (long long)(j0 + jb) * lda + j0; g.lda = lda; g.strideA = strideA;
-                g.B = pa.Tlo; g.ldb = NB; g.strideB = strideT;
-                g.C = Akk + (long long)(j0 + jb) * lda + j0; g.ldc = lda; g.strideC = strideA;
-                g.Ct = Akk + (long long)j0 * lda + (j0 + jb); g.ldct = lda; g.strideCt = strideA;
-                g.M = m; g.N = jb; g.K = jb; g.batch = batch;
-                rc = launch_gemm_nt(g, stream);
-                if (rc) return rc;
-                GemmDesc h = gemm_desc();
-                h.A = g.C; h.lda = lda; h.strideA = strideA;
-                h.B = g.C; h.ldb = lda; h.strideB = strideA;
-                h.C = Akk + (long long)(j0 + jb) * (lda + 1); h.ldc = lda; h.strideC = strideA;
-                h.M = m; h.N = m; h.K = jb; h.alpha = -1.0; h.beta = 1.0; h.lower = 1; h.batch = batch;
-                rc = launch_gemm_nt(h, stream);
-                if (rc) return rc;
-            }
-        }
-        // ---- inverse of the NB diagonal block by doubling (also for the last block: the compact
-        //      inverses are what the row solves and the triangular inverse start from)
-        const int r0 = k + nbk;
-        const int M = nrows - r0;
-        for (int s = PT; s < nbk; s *= 2) {
-            // scratch: the strictly-upper part of W is free here (W is consumed only by the panel solve)
-            rc = doubling_level(Akk, lda, strideA, Tlo_k, Tup_k, NB, strideT, W, NB, strideW, nbk, s, batch,
-                                stream);
-            if (rc) return rc;
-        }
+    for (int j0 = 0; j0 < gw; j0 += PT) {
+        const int jb = min(PT, gw - j0), col = k0 + j0, rb = col + jb;
+        Potf2Args pa;
+        pa.A = c.A + (long long)col * (lda + 1); pa.lda = lda; pa.strideA = c.strideA;
+        pa.Tlo = Tlo_k + (long long)j0 * (NB + 1); pa.Tup = Tup_k + (long long)j0 * (NB + 1);
+        pa.ldt = NB; pa.strideT = c.strideT; pa.nb = jb; pa.info = c.info; pa.strideInfo = c.strideInfo;
+        pa.row0 = col; pa.dbg = nullptr;
+        rc = launch_potf2(pa, c.batch, stream);
+        if (rc) return rc;
+        const int M = c.nrows - rb;
         if (M <= 0) break;
-        // ---- panel solve: rows r0..nrows-1 of columns k..k+nbk
-        double* P = A + (long long)r0 * lda + k;
-        const int mirror_rows = max(0, n - r0);
-        const double* Pnl;  // solved panel as GEMM operand
-        long long ldp, strideP;
-        if (nbk <= PT) {
-            GemmDesc g = gemm_desc();
-            g.A = P; g.lda = lda; g.strideA = strideA;
-            g.B = Tlo_k; g.ldb = NB; g.strideB = strideT;
-            g.C = P; g.ldc = lda; g.strideC = strideA;
-            g.M = M; g.N = nbk; g.K = nbk; g.batch = batch;
-            rc = launch_gemm_nt(g, stream);
-            if (rc) return rc;
-            if (mirror_rows > 0) {
-                CopyPanelArgs c;
-                c.W = P; c.ldw = lda; c.strideW = strideA; c.Alo = P; c.Aup = A + (long long)k * lda + r0;
-                c.lda = lda; c.strideA = strideA; c.rows = mirror_rows; c.cols = nbk; c.mirror_rows = mirror_rows;
-                rc = launch_copy_panel(c, batch, stream);
-                if (rc) return rc;
-            }
-            Pnl = P; ldp = lda; strideP = strideA;
-        } else {
-            GemmDesc g = gemm_desc();
-            g.A = P; g.lda = lda; g.strideA = strideA;
-            g.B = Tlo_k; g.ldb = NB; g.strideB = strideT;
-            g.C = W; g.ldc = NB; g.strideC = strideW;
-            g.M = M; g.N = nbk; g.K = nbk; g.krange = KR_TO_COL; g.batch = batch;
-            rc = launch_gemm_nt(g, stream);
-            if (rc) return rc;
-            CopyPanelArgs c;
-            c.W = W; c.ldw = NB; c.strideW = strideW; c.Alo = P; c.Aup = A + (long long)k * lda + r0;
-            c.lda = lda; c.strideA = strideA; c.rows = M; c.cols = nbk; c.mirror_rows = mirror_rows;
-            rc = launch_copy_panel(c, batch, stream);
-            if (rc) return rc;
-            Pnl = W; ldp = NB; strideP = strideW;
-        }
-        // ---- trailing update (lower tiles; the extra rows are the rectangular tail of the tile list)
-        const int Nn = n - r0;
-        if (Nn > 0) {
+        double* Pa = c.A + (long long)rb * lda + col;         // rows below the tile, in A
+        double* Pw = Wg + (long long)(rb - k0) * NB + j0;      // the same rows in the group panel buffer
+        GemmDesc g = gemm_desc();
+        g.A = Pa; g.lda = lda; g.strideA = c.strideA;
+        g.B = pa.Tlo; g.ldb = NB; g.strideB = c.strideT;
+        g.C = Pw; g.ldc = NB; g.strideC = strideW;
+        g.M = M; g.N = jb; g.K = jb; g.batch = c.batch;
+        rc = launch_gemm_nt(g, stream);
+        if (rc) return rc;
+        CopyPanelArgs cp;
+        cp.W = Pw; cp.ldw = NB; cp.strideW = strideW; cp.Alo = Pa; cp.Aup = c.A + (long long)col * lda + rb;
+        cp.lda = lda; cp.strideA = c.strideA; cp.rows = M; cp.cols = jb; cp.mirror_rows = max(0, c.n - rb);
+        rc = launch_copy_panel(cp, c.batch, stream);
+        if (rc) return rc;
+        const int Nrem = gw - (j0 + jb);  // columns of the group still to be factored
+        if (Nrem > 0) {
             GemmDesc h = gemm_desc();
-            h.A = Pnl; h.lda = ldp; h.strideA = strideP;
-            h.B = Pnl; h.ldb = ldp; h.strideB = strideP;
-            h.C = A + (long long)r0 * (lda + 1); h.ldc = lda; h.strideC = strideA;
-            h.M = M; h.N = Nn; h.K = nbk; h.alpha = -1.0; h.beta = 1.0; h.lower = 1; h.batch = batch;
+            h.A = Pw; h.lda = NB; h.strideA = strideW;
+            h.B = Pw; h.ldb = NB; h.strideB = strideW;
+            h.C = c.A + (long long)rb * (lda + 1); h.ldc = lda; h.strideC = c.strideA;
+            h.M = M; h.N = Nrem; h.K = jb; h.alpha = -1.0; h.beta = 1.0; h.lower = 1; h.batch = c.batch;
             rc = launch_gemm_nt(h, stream);
             if (rc) return rc;
         }
     }
     return GPMP_OK;
+}
+
+// NB-wide inverses of the diagonal blocks from the 128-tile inverses, by doubling; all full blocks of one
+// matrix go in one batched launch per level.  Xscr: scratch of >= nblk * NB * NB doubles per batch entry.
+static int block_inverses(const PotrfCtx& c, double* Xscr, long long strideX, cudaStream_t stream) {
+    const int NB = c.NB, n = c.n;
+    if (NB <= PT) return GPMP_OK;
+    const int nfull = n / NB, rem = n - nfull * NB;
+    int rc;
+    for (int s = PT; s < NB; s *= 2) {
+        if (c.batch == 1) {
+            if (nfull > 0) {
+                rc = doubling_level(c.A, c.lda, (long long)NB * (c.lda + 1), c.Tlo, c.Tup, NB, (long long)NB * NB,
+                                    Xscr, NB, (long long)NB * NB, NB, s, nfull, stream);
+                if (rc) return rc;
+            }
+        } else {
+            for (int b = 0; b < nfull; ++b) {
+                rc = doubling_level(c.A + (long long)b * NB * (c.lda + 1), c.lda, c.strideA,
+                                    c.Tlo + (long long)b * NB * NB, c.Tup + (long long)b * NB * NB, NB, c.strideT,
+                                    Xscr, NB, strideX, NB, s, c.batch, stream);
+                if (rc) return rc;
+            }
+        }
+        if (rem > s) {
+            rc = doubling_level(c.A + (long long)nfull * NB * (c.lda + 1), c.lda, c.strideA,
+                                c.Tlo + (long long)nfull * NB * NB, c.Tup + (long long)nfull * NB * NB, NB,
+                                c.strideT, Xscr, NB, strideX, rem, s, c.batch, stream);
+            if (rc) return rc;
+        }
+    }
+    return GPMP_OK;
+}
+
+// Trailing update with the solved panel of step k, restricted to the block columns [col0, col1) of the
+// trailing matrix (offsets relative to r0; col1 < 0: to the end).  Lower tiles; the extra rows are the
+// rectangular tail of the tile list.
+static int trailing_update(const PotrfCtx& c, int k, const double* Pnl, long long ldp, long long strideP,
+                           int col0, int col1, cudaStream_t stream) {
+    const int NB = c.NB, nbk = min(NB, c.n - k), r0 = k + nbk;
+    const int Nn = c.n - r0;
+    if (col1 < 0 || col1 > Nn) col1 = Nn;
+    if (col0 >= col1) return GPMP_OK;
+    const int M = c.nrows - r0 - col0;
+    GemmDesc h = gemm_desc();
+    h.A = Pnl + (long long)col0 * ldp; h.lda = ldp; h.strideA = strideP;
+    h.B = Pnl + (long long)col0 * ldp; h.ldb = ldp; h.strideB = strideP;
+    h.C = c.A + (long long)(r0 + col0) * (c.lda + 1); h.ldc = c.lda; h.strideC = c.strideA;
+    h.M = M; h.N = col1 - col0; h.K = nbk; h.alpha = -1.0; h.beta = 1.0; h.lower = 1; h.batch = c.batch;
+    return launch_gemm_nt(h, stream);
+}
+
+// Library-owned side stream (high priority) and events for the look-ahead pipeline.
+struct LookAhead {
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int dev = -1;
+    bool ok = false;
+};
+static LookAhead& lookahead(int nevents) {
+    static LookAhead la;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (la.side == nullptr || la.dev != dev) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi) == cudaSuccess;
+        la.dev = dev;
+        la.ev.clear();
+    }
+    while (la.ok && (int)la.ev.size() < nevents) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { la.ok = false; break; }
+        la.ev.push_back(e);
+    }
+    return la;
+}
+
+// Core factorisation.
+//   A      (nrows x lda)            in: lower of K (+ extra rows); out: L both-ways (+ whitened rows)
+//   Tlo/Tup compact diagonal-block inverses: nblk blocks of NB x NB (ld NB), block b at b*NB*NB
+//   W      panel scratch: TWO buffers of max(nrows, NB) x NB (ld NB) per batch entry, the second at
+//          W + Wrows*NB (look-ahead keeps the previous group's panel alive while the next one is built)
+// Single matrices with several column groups run a depth-1 look-ahead: the main stream does the bulk of
+// every K=NB trailing update while a high-priority side stream updates the next group's columns and
+// runs its 128-wide steps, so the latency-bound chain hides behind the big SYRK.
+int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
+               long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
+               cudaStream_t stream) {
+    if (n <= 0) return GPMP_OK;
+    PotrfCtx c{A, lda, strideA, n, nrows, NB, Tlo, Tup, strideT, info, strideInfo, batch};
+    const int nblk = ceil_div(n, NB);
+    const long long wrows = nrows > NB ? nrows : NB;
+    double* Wb[2] = {W, W + wrows * NB};
+    int rc;
+    const bool pipelined = batch == 1 && nblk >= 3 && NB > PT;
+    LookAhead* la = pipelined ? &lookahead(2 * nblk + 4) : nullptr;
+    if (!pipelined || !la->ok) {
+        for (int k = 0; k < n; k += NB) {
+            const int gw = min(NB, n - k), r0 = k + gw;
+            rc = group_panel(c, k, Wb[0], strideW, stream);
+            if (rc) return rc;
+            if (nrows - r0 <= 0) break;
+            rc = trailing_update(c, k, Wb[0] + (long long)gw * NB, NB, strideW, 0, -1, stream);
+            if (rc) return rc;
+        }
+        return block_inverses(c, Wb[0], strideW, stream);
+    }
+    cudaStream_t s = stream, B = la->side;
+    auto evPanel = [&](int b) { return la->ev[2 + b]; };
+    auto evRest = [&](int b) { return la->ev[2 + nblk + b]; };
+    // fork
+    if (cudaEventRecord(la->ev[0], s) != cudaSuccess || cudaStreamWaitEvent(B, la->ev[0], 0) != cudaSuccess)
+        return GPMP_ERR_CUDA;
+    rc = group_panel(c, 0, Wb[0], strideW, B);
+    if (rc) return rc;
+    cudaEventRecord(evPanel(0), B);
+    for (int b = 0; b < nblk; ++b) {
+        const int k = b * NB, gw = min(NB, n - k), r0 = k + gw;
+        if (nrows - r0 <= 0) break;
+        const double* Pk = Wb[b & 1] + (long long)gw * NB;  // solved panel rows r0.. of group b
+        const int nb_next = min(NB, n - r0);  // width of the next group (0 when only extra rows remain)
+        // head: the next group's columns, on the side stream (after the previous bulk update touched them)
+        if (b > 0) cudaStreamWaitEvent(B, evRest(b - 1), 0);
+        if (nb_next > 0) {
+            rc = trailing_update(c, k, Pk, NB, strideW, 0, nb_next, B);
+            if (rc) return rc;
+        }
+        // bulk of the trailing update on the main stream
+        cudaStreamWaitEvent(s, evPanel(b), 0);
+        rc = trailing_update(c, k, Pk, NB, strideW, nb_next, -1, s);
+        if (rc) return rc;
+        cudaEventRecord(evRest(b), s);
+        // next group on the side stream
+        if (nb_next > 0) {
+            rc = group_panel(c, r0, Wb[(b + 1) & 1], strideW, B);
+            if (rc) return rc;
+            cudaEventRecord(evPanel(b + 1), B);
+        }
+    }
+    // join
+    if (cudaEventRecord(la->ev[1], B) != cudaSuccess || cudaStreamWaitEvent(s, la->ev[1], 0) != cudaSuccess)
+        return GPMP_ERR_CUDA;
+    return block_inverses(c, Wb[0], strideW, s);
 }
 
 // ---- potri: Tlo/Tup (n x n) from L and the compact NB-block inverses, then Kinv = T^T T (lower) ----

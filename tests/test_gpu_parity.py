@@ -37,7 +37,7 @@ def _cov_callable(gp, p, noise):
         s2, t2, lir = torch.exp(cp[0]), torch.exp(cp[1]), cp[2:]
         if y is x or y is None:
             if pairwise:
-                return (s2 + t2) * gnp.ones((x.shape[0],))
+                return s2 * gnp.ones((x.shape[0],))
             D = gnp.scaled_distance(lir, x, x)
             return s2 * gp.kernel.maternp_kernel(p, D) + t2 * gnp.eye(x.shape[0])
         if pairwise:
@@ -223,11 +223,11 @@ def test_likelihoods_and_gradients(gp, golden_np, golden_t, case):
 
 
 def test_likelihood_not_pd_gives_inf(gp):
-    x = np.zeros((40, 2))  # identical points: K = sigma2 (11^T + 10 eps I) -> not PD in floating point
+    x = np.random.default_rng(0).uniform(size=(40, 2))
     z = np.arange(40.0)
     m = gp.core.Model(cases.mean_fn("const", gp.num),
                       lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, 2, cp, pairwise))
-    th = torch.tensor([0.0, 0.0, 0.0], requires_grad=True)
+    th = torch.tensor([-800.0, 0.0, 0.0], requires_grad=True)  # sigma2 = exp(-800) = 0: K == 0, not PD
     v = m.negative_log_restricted_likelihood(th, x, z)
     assert torch.isinf(v) and v > 0
     val, grad = gp.num.value_and_grad(lambda t: m.negative_log_restricted_likelihood(t, x, z), th)
