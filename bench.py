@@ -39,6 +39,9 @@ sys.path.insert(0, ROOT)
 N_OBS, DIM, P_MATERN, SEED = 8192, 8, 2, 1234
 METRIC = "REML logL+grad evals/s (n=8192,d=8,fp64)"
 FP64_NOMINAL_TFLOPS = 40.0  # HGX B200 datasheet; MEASURED_PEAKS.json carries no fp64 entry
+# DRAM bytes of all DMMA GEMM launches of one evaluation (dram__bytes_read.sum + dram__bytes_write.sum summed
+# over the 154 launches, ncu capture committed as profiles/r01_gemm_dram_one_eval.csv)
+GEMM_DRAM_BYTES_PER_STEP = 5.634e9 + 1.273e9
 
 
 def headline_inputs(n=N_OBS, d=DIM, seed=SEED):
@@ -128,15 +131,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_s = 2048
+    # full size when the run stays within a few minutes (one evaluation is ~7-25 s of host time),
+    # otherwise n = 4096 scaled by n^3 (the O(n^2 d) terms make the scaled figure slightly pessimistic)
+    n_s = N_OBS if (args.steps + args.warmup) <= 8 else 4096
     scale = (N_OBS / n_s) ** 3
     for _ in range(args.warmup):
         cpu_eval_seconds(n_s, DIM)
     ts = [cpu_eval_seconds(n_s, DIM)[0] for _ in range(args.steps)]
     total = sum(ts)
     value = args.steps / (total * scale)
-    sample = (f"each step = 1 REML value+grad at n={n_s},d={DIM} (torch-CPU autograd, oracle port), "
-              f"time scaled by (8192/{n_s})^3={scale:.0f} to the n=8192 workload")
+    sample = (f"each step = 1 REML value+grad at n={n_s},d={DIM} (torch-CPU autograd, oracle port)"
+              + ("" if n_s == N_OBS else f", time scaled by (8192/{n_s})^3={scale:.0f} to the n=8192 workload"))
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
@@ -259,7 +264,8 @@ def run_gpu(args):
 
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
-        "frac": achieved / FP64_NOMINAL_TFLOPS, "traffic": None,
+        "frac": achieved / FP64_NOMINAL_TFLOPS, "traffic": GEMM_DRAM_BYTES_PER_STEP,
+        "traffic_note": "bytes per step over all launches of the kernel (profiles/r01_gemm_dram_one_eval.csv)",
         "kernel": "gpmp::gemm_nt_kernel (FP64 DMMA.8x8x4)",
         "peak_source": "nominal HGX B200 FP64 (MEASURED_PEAKS.json has no fp64 entry); cuBLAS dgemm 4096^3 "
                        f"measured in this run: {cublas_tf:.1f} TFLOP/s",

@@ -5,12 +5,12 @@
 // and the whitening/conditioning GEMMs of predict.  Every product on the path is arranged so that
 // both operands are read with K contiguous (row-major "K-major" tiles), see DESIGN.md.
 //
-// Two tile shapes of the same template:
-//   big    CTA 128x128, 16 warps as 4(M) x 4(N), warp tile 32x32 = 4x4 DMMA tiles (64 accumulator regs,
-//          4 warps per scheduler), 3 stages x 2 K-chunks of 16 (192 KB: one barrier per 32 k) -- the
-//          throughput shape (measured: same 31.5 TFLOP/s as 8 warps of 64x32 at large K, +8..25% at K<=512);
-//   small  CTA 64x64, 4 warps as 2 x 2, warp tile 32x32, 96 KB, 2 CTAs/SM -- for the latency-bound
-//          products inside a diagonal block, where a handful of 128-tiles would leave 140 SMs idle.
+// Two tile shapes of the same template (warp tile 32x32 = 4x4 DMMA tiles, 64 accumulator registers):
+//   default CTA 64x64, 4 warps as 2 x 2, 4-stage cp.async pipeline of 16-k chunks (64 KB), 3 CTAs per SM:
+//           independent CTAs cover each other's barrier / fragment-load bubbles, and small products
+//           (a handful of tiles inside a diagonal block) still spread over many SMs;
+//   wide    CTA 128x128, 16 warps as 4 x 4, 3 stages x 2 chunks (192 KB), 1 CTA per SM: only for in-place
+//           products, which need a single column tile per row block.
 // Shared tiles are dense 128-byte rows with the 16-byte chunk index XOR-swizzled by (row & 7) -- the
 // layout a TMA SWIZZLE_128B box produces.  Inside a K chunk the k index is permuted (lane kk owns
 // k = 4*kk + s at MMA step s) so each lane fetches its 4 steps with two conflict-free LDS.128.
@@ -19,7 +19,7 @@
 
 namespace gpmp {
 
-constexpr int BK = 16, STAGES = 3, SUBK = 2;
+constexpr int BK = 16;
 constexpr int KGRAN = 128;  // granularity of the triangular K trimming (the tile grid of the operands)
 
 struct GemmKArgs {
@@ -67,7 +67,7 @@ __device__ __forceinline__ void load_tile(uint32_t sdst, const double* __restric
     }
 }
 
-template <int WM, int WN, int MI, int NI>
+template <int WM, int WN, int MI, int NI, int STAGES, int SUBK>
 struct GemmCfg {
     static constexpr int BM = WM * MI * 8, BN = WN * NI * 8, THREADS = WM * WN * 32;
     static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
@@ -76,9 +76,9 @@ struct GemmCfg {
     static constexpr int SMEM = STAGES * STAGE_BYTES;
 };
 
-template <int WM, int WN, int MI, int NI, int MINB>
+template <int WM, int WN, int MI, int NI, int MINB, int STAGES, int SUBK>
 __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKArgs a) {
-    using Cfg = GemmCfg<WM, WN, MI, NI>;
+    using Cfg = GemmCfg<WM, WN, MI, NI, STAGES, SUBK>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS;
     extern __shared__ __align__(1024) unsigned char smem[];
     const GemmDesc& g = a.g;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKA
             if (nx < nk) load_stage(nx % STAGES, nx);
             cp_async_commit();
         }
-#pragma unroll 1
+#pragma unroll
         for (int u = 0; u < SUBK; ++u) {
             const unsigned char* st = smem + (kt % STAGES) * Cfg::STAGE_BYTES + u * Cfg::SUB_BYTES;
             double af[MI][4];
@@ -151,16 +151,22 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKA
                 const double2 v1 = *reinterpret_cast<const double2*>(st + aoff + mi * 1024 + c1);
                 af[mi][0] = v0.x; af[mi][1] = v0.y; af[mi][2] = v1.x; af[mi][3] = v1.y;
             }
+            double bf[NI][4];
 #pragma unroll
             for (int ni = 0; ni < NI; ++ni) {
                 const double2 w0 = *reinterpret_cast<const double2*>(st + boff + ni * 1024 + c0);
                 const double2 w1 = *reinterpret_cast<const double2*>(st + boff + ni * 1024 + c1);
-                const double bf[4] = {w0.x, w0.y, w1.x, w1.y};
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-#pragma unroll
-                    for (int mi = 0; mi < MI; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][s], bf[s]);
+                bf[ni][0] = w0.x; bf[ni][1] = w0.y; bf[ni][2] = w1.x; bf[ni][3] = w1.y;
             }
+            // k-step outermost: an accumulator is revisited only after MI*NI other DMMAs, so the pipe never
+            // waits on its own result
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi)
+                        dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][s], bf[ni][s]);
         }
     }
     cp_async_wait<0>();
@@ -198,11 +204,11 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKA
     }
 }
 
-template <int WM, int WN, int MI, int NI, int MINB>
+template <int WM, int WN, int MI, int NI, int MINB, int STAGES = 3, int SUBK = 2>
 static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
-    using Cfg = GemmCfg<WM, WN, MI, NI>;
+    using Cfg = GemmCfg<WM, WN, MI, NI, STAGES, SUBK>;
     static bool configured = false;
-    auto kern = gemm_nt_kernel<WM, WN, MI, NI, MINB>;
+    auto kern = gemm_nt_kernel<WM, WN, MI, NI, MINB, STAGES, SUBK>;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
             return GPMP_ERR_CUDA;
@@ -237,20 +243,21 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
         return GPMP_ERR_ALIGN;
     if ((g.strideA & 1) || (g.strideB & 1) || (g.strideC & 1)) return GPMP_ERR_ALIGN;
     if ((g.stride2A & 1) || (g.stride2B & 1) || (g.stride2C & 1)) return GPMP_ERR_ALIGN;
-    // fewer 128-tiles than SMs: spread the work over 4x as many 64-tiles.  An in-place product (the
-    // single-column-tile panel solves) must keep one column tile per row block.
-    long long t128 = (long long)ceil_div(g.M, 128) * ceil_div(g.N, 128);
-    if (g.lower) t128 = t128 / 2 + ceil_div(g.N, 128);
-    t128 *= (long long)g.batch * g.batch2;
+    // Shape choice (measured on B200, TFLOP/s at K = 128 / 512 / 8192):
+    //   64x64 tiles, 4 warps, 4 stages x 16 k (64 KB), 3 CTAs/SM      21.3 / 30.5 / 32.9   <- default
+    //   128x128 tiles, 16 warps, 3 stages x 32 k (192 KB), 1 CTA/SM   18.5 / 25.8 / 32.0
+    // Several independent CTAs per SM hide each other's barrier and fragment-load bubbles, which a single
+    // big CTA cannot (the DMMA pipe sat at 85 % with 1 CTA/SM).  An in-place product (the single-column-tile
+    // panel solves, A == C) must keep one column tile per row block, so N > 64 takes the 128-wide shape.
     const bool in_place = (g.A == g.C || g.B == g.C);
-    if (t128 < 100 && !(in_place && g.N > 64)) return launch_cfg<2, 2, 4, 4, 2>(g, stream);
     static int big_cfg = -1;
     if (big_cfg < 0) {
         const char* e = getenv("GPMP_GEMM_CFG");
-        big_cfg = e ? atoi(e) : 1;
+        big_cfg = e ? atoi(e) : 4;
     }
-    if (big_cfg == 0) return launch_cfg<2, 4, 8, 4, 1>(g, stream);  // 8 warps of 64x32 (development switch)
-    return launch_cfg<4, 4, 4, 4, 1>(g, stream);
+    if (in_place && g.N > 64) return launch_cfg<4, 4, 4, 4, 1>(g, stream);
+    if (big_cfg == 1) return launch_cfg<4, 4, 4, 4, 1>(g, stream);  // development switch
+    return launch_cfg<2, 2, 4, 4, 3, 4, 1>(g, stream);
 }
 
 }  // namespace gpmp
