@@ -67,6 +67,7 @@ SIGNATURES = {
     "gpmp_lik_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gpmp_lik_value": (_i, [_specp, _vp, _ll, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp]),
     "gpmp_lik_grad": (_i, [_specp, _vp, _i, _i, _vp, _sz, _vp, _vp, _vp, _ll, _vp]),
+    "gpmp_lik_loo": (_i, [_i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "gpmp_predict_scratch_bytes": (_sz, [_i, _i, _i]),
     "gpmp_predict_chunk": (_i, [_specp, _vp, _i, _i, _vp, _sz, _vp, _i, _vp, _vp, _vp, _ll, _vp, _sz, _vp, _vp,
                                 _i, _vp]),

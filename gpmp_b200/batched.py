@@ -35,11 +35,17 @@ class BatchedCriterion:
         self.z = z.contiguous()
         self.group = group
         self.max_bytes = max_bytes
+        self._work = None  # device workspace, allocated at the first sweep and reused
 
     def values_device(self, thetas):
         """thetas: (N, 1+noise+d) array-like -> (values, info) device tensors for the local shard."""
         th = ops.to_device(thetas)
-        return ops.criterion_batched(th, self.x, self.z, self.P, self.p, self.noise, self.max_bytes)
+        n = self.x.shape[0]
+        q = 0 if self.P is None else self.P.shape[1]
+        if self._work is None or self._rows < th.shape[0]:
+            self._work = ops.criterion_batched_workspace(n, q, th.shape[0], self.max_bytes)
+            self._rows = th.shape[0]
+        return ops.criterion_batched(th, self.x, self.z, self.P, self.p, self.noise, self.max_bytes, self._work)
 
     def __call__(self, thetas, convert_out=True):
         th = np.asarray(thetas.detach().cpu() if torch.is_tensor(thetas) else thetas, dtype=np.float64)

@@ -139,21 +139,45 @@ class Model:
         return torch.tensor(ops.read_small(out)[2], dtype=torch.float64)
 
     # ------------------------------------------------------------------ prediction
-    def _fit(self, xi, zi, P, covparam):
+    def _fit(self, xi, zi, P, covparam, with_inverse=False):
         """Factor K(xi, xi) with zi (and P) whitened along -> (FitState, out_dev)."""
         K, fused = self._same_set_cov(xi, covparam)
         if fused:
             vals = ops.host_values(K.param)
             spec = ops._spec_from_param(K.p, xi.shape[1], vals)
-            state, out = ops.lik_value(spec, None, xi, zi, P, False)
+            state, out = ops.lik_value(spec, None, xi, zi, P, with_inverse)
             state.kernel = (K.p, K.param)
         else:
             Kd = kernel.materialize(K)
             Kd = Kd.detach()
             Kd = Kd if Kd.stride(1) == 1 else Kd.contiguous()
-            state, out = ops.lik_value(None, Kd, None, zi, P, False)
+            state, out = ops.lik_value(None, Kd, None, zi, P, with_inverse)
             state.kernel = None
         return state, out
+
+    # ------------------------------------------------------------------ leave-one-out
+    def loo(self, xi, zi, convert_in=True, convert_out=False):
+        """Leave-one-out predictions, variances and errors by virtual cross-validation
+        (core/model.py:309-343, core/loo.py:65-130), from the K^-1 / Pi the gradient pipeline builds."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi, convert=convert_in)
+        covparam = _as_param(self.covparam)
+        P = None
+        zc, prior = zi, None
+        if self.meantype == "linear_predictor":
+            P = self._basis(xi)
+        elif self.meantype == "parameterized":
+            prior = ops.to_device(self.mean(xi, _as_param(self.meanparam))).reshape(-1)
+            zc = zi - prior
+        with torch.no_grad():
+            state, out = self._fit(xi, zc, P, covparam, with_inverse=True)
+            if ops.read_small(out)[6] != 0.0:
+                raise torch.linalg.LinAlgError("loo: K(xi, xi) is not positive-definite")
+            zloo, s2, e = ops.lik_loo(state, zc.contiguous())
+            if prior is not None:
+                zloo = zloo + prior
+        if convert_out:
+            return num.to_np(zloo), num.to_np(s2), num.to_np(e)
+        return zloo, s2, e
 
     def predict(self, xi, zi, xt, return_lambdas=False, zero_neg_variances=True, convert_in=True,
                 convert_out=True):

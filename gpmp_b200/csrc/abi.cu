@@ -345,6 +345,31 @@ int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, 
     return GPMP_OK;
 }
 
+int gpmp_lik_loo(int n, int q, void* work_dev, size_t work_bytes, const double* z_dev, double* zloo_dev,
+                 double* s2loo_dev, double* eloo_dev, void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !z_dev || !zloo_dev || !s2loo_dev || !eloo_dev)
+        return GPMP_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    LikWs w = lik_ws(n, q, 1);
+    if (work_bytes < w.total_grad - (w.total_grad - w.off_partial)) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    double* A = (double*)(base + w.off_A);
+    char* pb = base + w.off_potrf;
+    double* Tlo = (double*)(base + w.off_Tlo);
+    double* Tup = (double*)(base + w.off_Tup);
+    double* Kinv = (double*)(base + w.off_Kinv);
+    double* U = (double*)(base + w.off_U);
+    int rc = potri_core(A, n, w.lda, w.pw.NB, (const double*)(pb + w.pw.off_tlo), (const double*)(pb + w.pw.off_tup),
+                        Tlo, Tup, Kinv, w.lda, s);
+    if (rc) return rc;
+    URowsArgs u;
+    u.R = A + (long long)n * w.lda; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;
+    u.n = n;
+    rc = launch_urows(u, s);
+    if (rc) return rc;
+    return launch_loo(Kinv, w.lda, U, w.lda, q, n, z_dev, zloo_dev, s2loo_dev, eloo_dev, s);
+}
+
 // ---- prediction -----------------------------------------------------------------------------------
 size_t gpmp_predict_scratch_bytes(int n, int q, int m) {
     const int NB = potrf_block_size(n);

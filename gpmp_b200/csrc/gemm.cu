@@ -6,7 +6,7 @@
 // both operands are read with K contiguous (row-major "K-major" tiles), see DESIGN.md.
 //
 // Two tile shapes of the same template (warp tile 32x32 = 4x4 DMMA tiles, 64 accumulator registers):
-//   default CTA 64x64, 4 warps as 2 x 2, 4-stage cp.async pipeline of 16-k chunks (64 KB), 3 CTAs per SM:
+//   default CTA 64x64, 4 warps as 2 x 2, 3-stage cp.async pipeline of 16-k chunks (48 KB), 4 CTAs per SM:
 //           independent CTAs cover each other's barrier / fragment-load bubbles, and small products
 //           (a handful of tiles inside a diagonal block) still spread over many SMs;
 //   wide    CTA 128x128, 16 warps as 4 x 4, 3 stages x 2 chunks (192 KB), 1 CTA per SM: only for in-place
@@ -244,7 +244,8 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
     if ((g.strideA & 1) || (g.strideB & 1) || (g.strideC & 1)) return GPMP_ERR_ALIGN;
     if ((g.stride2A & 1) || (g.stride2B & 1) || (g.stride2C & 1)) return GPMP_ERR_ALIGN;
     // Shape choice (measured on B200, TFLOP/s at K = 128 / 512 / 8192):
-    //   64x64 tiles, 4 warps, 4 stages x 16 k (64 KB), 3 CTAs/SM      21.3 / 30.5 / 32.9   <- default
+    //   64x64 tiles, 4 warps, 3 stages x 16 k (48 KB), 4 CTAs/SM      24.1 / 30.9 / 32.8   <- default
+    //   64x64 tiles, 4 warps, 4 stages x 16 k (64 KB), 3 CTAs/SM      21.3 / 30.5 / 32.9
     //   128x128 tiles, 16 warps, 3 stages x 32 k (192 KB), 1 CTA/SM   18.5 / 25.8 / 32.0
     // Several independent CTAs per SM hide each other's barrier and fragment-load bubbles, which a single
     // big CTA cannot (the DMMA pipe sat at 85 % with 1 CTA/SM).  An in-place product (the single-column-tile
@@ -253,11 +254,12 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
     static int big_cfg = -1;
     if (big_cfg < 0) {
         const char* e = getenv("GPMP_GEMM_CFG");
-        big_cfg = e ? atoi(e) : 4;
+        big_cfg = e ? atoi(e) : 6;
     }
     if (in_place && g.N > 64) return launch_cfg<4, 4, 4, 4, 1>(g, stream);
     if (big_cfg == 1) return launch_cfg<4, 4, 4, 4, 1>(g, stream);  // development switch
-    return launch_cfg<2, 2, 4, 4, 3, 4, 1>(g, stream);
+    if (big_cfg == 4) return launch_cfg<2, 2, 4, 4, 3, 4, 1>(g, stream);  // 3 CTAs/SM, 4 stages (development)
+    return launch_cfg<2, 2, 4, 4, 4, 3, 1>(g, stream);
 }
 
 }  // namespace gpmp

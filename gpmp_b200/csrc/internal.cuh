@@ -81,6 +81,8 @@ int launch_logdet_r0(const double* p0rows, double* p0work, long long ld, int n, 
                      cudaStream_t stream);
 int launch_urows(const URowsArgs& a, cudaStream_t stream);
 int launch_dense_grad(const DenseGradArgs& a, cudaStream_t stream);
+int launch_loo(const double* Kinv, long long ldk, const double* U, long long ldu, int q, int n, const double* z,
+               double* zloo, double* s2loo, double* eloo, cudaStream_t stream);
 
 // ---- predict.cu
 struct RowDotsArgs {

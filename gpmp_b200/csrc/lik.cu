@@ -237,6 +237,33 @@ int launch_urows(const URowsArgs& a, cudaStream_t stream) {
     return GPMP_OK;
 }
 
+// ---- leave-one-out by virtual cross-validation (core/loo.py:65-130): diag(Pi) and Pi z from K^-1 and U ----
+struct LooArgs {
+    const double* Kinv; long long ldk; const double* U; long long ldu; int q, n;
+    const double* z; double* zloo; double* s2loo; double* eloo;
+};
+__global__ void loo_kernel(const LooArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double dg = a.Kinv[(long long)i * (a.ldk + 1)];
+    for (int c = 0; c < a.q; ++c) {
+        const double u = a.U[(long long)c * a.ldu + i];
+        dg = fma(-u, u, dg);
+    }
+    const double e = a.U[(long long)a.q * a.ldu + i] / dg;  // (Pi z)_i / Pi_ii
+    a.eloo[i] = e;
+    a.s2loo[i] = 1.0 / dg;
+    a.zloo[i] = a.z[i] - e;
+}
+int launch_loo(const double* Kinv, long long ldk, const double* U, long long ldu, int q, int n, const double* z,
+               double* zloo, double* s2loo, double* eloo, cudaStream_t stream) {
+    LooArgs a{Kinv, ldk, U, ldu, q, n, z, zloo, s2loo, eloo};
+    LaunchScope scope(KC_SMALL, 0.0, stream);
+    loo_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
 // ---- dense dvalue/dK = 0.5 (K^-1 - U^T U) for the composable path (user-built covariance) ------------
 __global__ void __launch_bounds__(256) dense_grad_kernel(const DenseGradArgs a) {
     __shared__ double ui[GPMP_MAX_Q + 1][32], uj[GPMP_MAX_Q + 1][32];

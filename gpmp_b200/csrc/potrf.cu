@@ -57,12 +57,16 @@ __device__ __forceinline__ void smem_mma(int M8, int N8, int wid, int nw, FA a, 
             av[s] = a(i, 4 * s + kk);
             bv[s] = b(j, 4 * s + kk);
         }
-        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        // four independent accumulator pairs: the DMMA dependency chain is K/16 deep instead of K/4
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
 #pragma unroll
-        for (int s = 0; s < K / 4; s += 2) {  // two independent accumulator pairs hide the DMMA latency
+        for (int s = 0; s < K / 4; s += 4) {
             dmma884(c0, c1, av[s], bv[s]);
             if (s + 1 < K / 4) dmma884(d0, d1, av[s + 1], bv[s + 1]);
+            if (s + 2 < K / 4) dmma884(e0, e1, av[s + 2], bv[s + 2]);
+            if (s + 3 < K / 4) dmma884(f0, f1, av[s + 3], bv[s + 3]);
         }
+        c0 += e0; c1 += e1; d0 += f0; d1 += f1;
         out(i, j8 * 8 + 2 * kk, c0 + d0, c1 + d1);
     }
 }
@@ -515,47 +519,64 @@ struct PotrfCtx {
 // the loop ends the buffer holds the complete solved panel of the group: W[(r - k0)][j] = L[r][k0 + j] for
 // every row r below the tile of column j (rows n..nrows-1 included), so no NB-wide triangular solve and no
 // NB-wide block inverse sit on the critical path (the inverses are doubled up after the factorisation).
-static int group_panel(const PotrfCtx& c, int k0, double* Wg, long long strideW, cudaStream_t stream) {
+// One 128-wide step of the group starting at k0: tile factor+inverse, solve of all rows below (into the
+// group panel buffer), copy-back + mirror.
+static int tile_step(const PotrfCtx& c, int k0, int j0, double* Wg, long long strideW, cudaStream_t stream) {
     const int NB = c.NB, gw = min(NB, c.n - k0);
     const long long lda = c.lda;
     double* Tlo_k = c.Tlo + (long long)(k0 / NB) * NB * NB;
     double* Tup_k = c.Tup + (long long)(k0 / NB) * NB * NB;
-    int rc;
+    const int jb = min(PT, gw - j0), col = k0 + j0, rb = col + jb;
+    Potf2Args pa;
+    pa.A = c.A + (long long)col * (lda + 1); pa.lda = lda; pa.strideA = c.strideA;
+    pa.Tlo = Tlo_k + (long long)j0 * (NB + 1); pa.Tup = Tup_k + (long long)j0 * (NB + 1);
+    pa.ldt = NB; pa.strideT = c.strideT; pa.nb = jb; pa.info = c.info; pa.strideInfo = c.strideInfo;
+    pa.row0 = col; pa.dbg = nullptr;
+    int rc = launch_potf2(pa, c.batch, stream);
+    if (rc) return rc;
+    const int M = c.nrows - rb;
+    if (M <= 0) return GPMP_OK;
+    double* Pa = c.A + (long long)rb * lda + col;         // rows below the tile, in A
+    double* Pw = Wg + (long long)(rb - k0) * NB + j0;      // the same rows in the group panel buffer
+    GemmDesc g = gemm_desc();
+    g.A = Pa; g.lda = lda; g.strideA = c.strideA;
+    g.B = pa.Tlo; g.ldb = NB; g.strideB = c.strideT;
+    g.C = Pw; g.ldc = NB; g.strideC = strideW;
+    g.M = M; g.N = jb; g.K = jb; g.batch = c.batch;
+    rc = launch_gemm_nt(g, stream);
+    if (rc) return rc;
+    CopyPanelArgs cp;
+    cp.W = Pw; cp.ldw = NB; cp.strideW = strideW; cp.Alo = Pa; cp.Aup = c.A + (long long)col * lda + rb;
+    cp.lda = lda; cp.strideA = c.strideA; cp.rows = M; cp.cols = jb; cp.mirror_rows = max(0, c.n - rb);
+    return launch_copy_panel(cp, c.batch, stream);
+}
+
+// K=128 update inside the group starting at k0: the solved step at j0 updates the group's columns
+// [c0, c1) (offsets inside the group, multiples of 128, c0 > j0), all rows from c0 down.
+static int in_group_update(const PotrfCtx& c, int k0, int j0, int c0, int c1, double* Wg, long long strideW,
+                           cudaStream_t stream) {
+    const int NB = c.NB, gw = min(NB, c.n - k0);
+    c1 = min(c1, gw);
+    if (c0 >= c1) return GPMP_OK;
+    const int jb = min(PT, gw - j0), R = k0 + c0, M = c.nrows - R;
+    if (M <= 0) return GPMP_OK;
+    const double* Pw = Wg + (long long)c0 * NB + j0;
+    GemmDesc h = gemm_desc();
+    h.A = Pw; h.lda = NB; h.strideA = strideW;
+    h.B = Pw; h.ldb = NB; h.strideB = strideW;
+    h.C = c.A + (long long)R * (c.lda + 1); h.ldc = c.lda; h.strideC = c.strideA;
+    h.M = M; h.N = c1 - c0; h.K = jb; h.alpha = -1.0; h.beta = 1.0; h.lower = 1; h.batch = c.batch;
+    return launch_gemm_nt(h, stream);
+}
+
+// Whole group on one stream (the non-pipelined path).
+static int group_panel(const PotrfCtx& c, int k0, double* Wg, long long strideW, cudaStream_t stream) {
+    const int gw = min(c.NB, c.n - k0);
     for (int j0 = 0; j0 < gw; j0 += PT) {
-        const int jb = min(PT, gw - j0), col = k0 + j0, rb = col + jb;
-        Potf2Args pa;
-        pa.A = c.A + (long long)col * (lda + 1); pa.lda = lda; pa.strideA = c.strideA;
-        pa.Tlo = Tlo_k + (long long)j0 * (NB + 1); pa.Tup = Tup_k + (long long)j0 * (NB + 1);
-        pa.ldt = NB; pa.strideT = c.strideT; pa.nb = jb; pa.info = c.info; pa.strideInfo = c.strideInfo;
-        pa.row0 = col; pa.dbg = nullptr;
-        rc = launch_potf2(pa, c.batch, stream);
+        int rc = tile_step(c, k0, j0, Wg, strideW, stream);
         if (rc) return rc;
-        const int M = c.nrows - rb;
-        if (M <= 0) break;
-        double* Pa = c.A + (long long)rb * lda + col;         // rows below the tile, in A
-        double* Pw = Wg + (long long)(rb - k0) * NB + j0;      // the same rows in the group panel buffer
-        GemmDesc g = gemm_desc();
-        g.A = Pa; g.lda = lda; g.strideA = c.strideA;
-        g.B = pa.Tlo; g.ldb = NB; g.strideB = c.strideT;
-        g.C = Pw; g.ldc = NB; g.strideC = strideW;
-        g.M = M; g.N = jb; g.K = jb; g.batch = c.batch;
-        rc = launch_gemm_nt(g, stream);
+        rc = in_group_update(c, k0, j0, j0 + PT, gw, Wg, strideW, stream);
         if (rc) return rc;
-        CopyPanelArgs cp;
-        cp.W = Pw; cp.ldw = NB; cp.strideW = strideW; cp.Alo = Pa; cp.Aup = c.A + (long long)col * lda + rb;
-        cp.lda = lda; cp.strideA = c.strideA; cp.rows = M; cp.cols = jb; cp.mirror_rows = max(0, c.n - rb);
-        rc = launch_copy_panel(cp, c.batch, stream);
-        if (rc) return rc;
-        const int Nrem = gw - (j0 + jb);  // columns of the group still to be factored
-        if (Nrem > 0) {
-            GemmDesc h = gemm_desc();
-            h.A = Pw; h.lda = NB; h.strideA = strideW;
-            h.B = Pw; h.ldb = NB; h.strideB = strideW;
-            h.C = c.A + (long long)rb * (lda + 1); h.ldc = lda; h.strideC = c.strideA;
-            h.M = M; h.N = Nrem; h.K = jb; h.alpha = -1.0; h.beta = 1.0; h.lower = 1; h.batch = c.batch;
-            rc = launch_gemm_nt(h, stream);
-            if (rc) return rc;
-        }
     }
     return GPMP_OK;
 }
@@ -612,7 +633,8 @@ static int trailing_update(const PotrfCtx& c, int k, const double* Pnl, long lon
 
 // Library-owned side stream (high priority) and events for the look-ahead pipeline.
 struct LookAhead {
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr;    // the chain: what the next tile factorisation is waiting for
+    cudaStream_t helper = nullptr;  // updates inside the next column group that are not on the chain
     std::vector<cudaEvent_t> ev;
     int dev = -1;
     bool ok = false;
@@ -624,7 +646,8 @@ static LookAhead& lookahead(int nevents) {
     if (la.side == nullptr || la.dev != dev) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi) == cudaSuccess;
+        la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                cudaStreamCreateWithPriority(&la.helper, cudaStreamNonBlocking, hi) == cudaSuccess;
         la.dev = dev;
         la.ev.clear();
     }
@@ -654,7 +677,7 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
     double* Wb[2] = {W, W + wrows * NB};
     int rc;
     const bool pipelined = batch == 1 && nblk >= 3 && NB > PT;
-    LookAhead* la = pipelined ? &lookahead(2 * nblk + 4) : nullptr;
+    LookAhead* la = pipelined ? &lookahead(3 + 10 * (nblk + 2)) : nullptr;
     if (!pipelined || !la->ok) {
         for (int k = 0; k < n; k += NB) {
             const int gw = min(NB, n - k), r0 = k + gw;
@@ -666,40 +689,83 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
         }
         return block_inverses(c, Wb[0], strideW, stream);
     }
-    cudaStream_t s = stream, B = la->side;
-    auto evPanel = [&](int b) { return la->ev[2 + b]; };
-    auto evRest = [&](int b) { return la->ev[2 + nblk + b]; };
+    // Three streams.  s (caller's): the bulk K=NB updates.  B (chain): only what the next tile factorisation
+    // waits for -- the update of the next 128 columns, the tile kernel, the solve below it.  H (helper): the
+    // other updates inside the next group (its remaining columns from the previous panel and from its own
+    // earlier steps).  Events order every read-modify-write of a column block.
+    cudaStream_t s = stream, B = la->side, H = la->helper;
+    const int EV = 10;
+    auto ev = [&](int g, int i) { return la->ev[2 + (g + 1) * EV + i]; };  // g = -1 .. nblk-1
+    enum { E_PANEL = 0, E_REST = 1, E_HEADREST = 2, E_TRSM = 3 /* +c, c<4 */, E_IN = 7 /* +c, c<2 */ };
+    // steps of the group starting at k0 (group index g); head_rest: wait for the helper's head update first
+    auto run_group = [&](int g, int k0, double* Wn, bool head_rest) -> int {
+        const int gw = min(NB, n - k0), nblocks = ceil_div(gw, PT);
+        for (int cb = 0; cb < nblocks; ++cb) {
+            const int j0 = cb * PT;
+            int rc2 = tile_step(c, k0, j0, Wn, strideW, B);
+            if (rc2) return rc2;
+            cudaEventRecord(ev(g, E_TRSM + cb), B);
+            if (cb + 1 < nblocks) {
+                if (cb == 0) {
+                    if (head_rest) cudaStreamWaitEvent(B, ev(g, E_HEADREST), 0);
+                } else {
+                    cudaStreamWaitEvent(B, ev(g, E_IN + cb - 1), 0);
+                }
+                rc2 = in_group_update(c, k0, j0, j0 + PT, j0 + 2 * PT, Wn, strideW, B);
+                if (rc2) return rc2;
+            }
+            if (cb + 2 < nblocks) {
+                cudaStreamWaitEvent(H, ev(g, E_TRSM + cb), 0);
+                rc2 = in_group_update(c, k0, j0, j0 + 2 * PT, gw, Wn, strideW, H);
+                if (rc2) return rc2;
+                cudaEventRecord(ev(g, E_IN + cb), H);
+            }
+        }
+        cudaEventRecord(ev(g, E_PANEL), B);
+        return GPMP_OK;
+    };
     // fork
-    if (cudaEventRecord(la->ev[0], s) != cudaSuccess || cudaStreamWaitEvent(B, la->ev[0], 0) != cudaSuccess)
+    if (cudaEventRecord(la->ev[0], s) != cudaSuccess || cudaStreamWaitEvent(B, la->ev[0], 0) != cudaSuccess ||
+        cudaStreamWaitEvent(H, la->ev[0], 0) != cudaSuccess)
         return GPMP_ERR_CUDA;
-    rc = group_panel(c, 0, Wb[0], strideW, B);
+    rc = run_group(0, 0, Wb[0], false);
     if (rc) return rc;
-    cudaEventRecord(evPanel(0), B);
     for (int b = 0; b < nblk; ++b) {
         const int k = b * NB, gw = min(NB, n - k), r0 = k + gw;
         if (nrows - r0 <= 0) break;
         const double* Pk = Wb[b & 1] + (long long)gw * NB;  // solved panel rows r0.. of group b
         const int nb_next = min(NB, n - r0);  // width of the next group (0 when only extra rows remain)
-        // head: the next group's columns, on the side stream (after the previous bulk update touched them)
-        if (b > 0) cudaStreamWaitEvent(B, evRest(b - 1), 0);
+        const int head0 = min(PT, nb_next);
+        // updates of the next group's columns by panel b: first 128 columns on the chain, the rest on the helper
+        if (b > 0) {
+            cudaStreamWaitEvent(B, ev(b - 1, E_REST), 0);
+            cudaStreamWaitEvent(H, ev(b - 1, E_REST), 0);
+        }
         if (nb_next > 0) {
-            rc = trailing_update(c, k, Pk, NB, strideW, 0, nb_next, B);
+            rc = trailing_update(c, k, Pk, NB, strideW, 0, head0, B);
             if (rc) return rc;
+            if (nb_next > head0) {
+                cudaStreamWaitEvent(H, ev(b, E_PANEL), 0);
+                rc = trailing_update(c, k, Pk, NB, strideW, head0, nb_next, H);
+                if (rc) return rc;
+                cudaEventRecord(ev(b + 1, E_HEADREST), H);
+            }
         }
         // bulk of the trailing update on the main stream
-        cudaStreamWaitEvent(s, evPanel(b), 0);
+        cudaStreamWaitEvent(s, ev(b, E_PANEL), 0);
         rc = trailing_update(c, k, Pk, NB, strideW, nb_next, -1, s);
         if (rc) return rc;
-        cudaEventRecord(evRest(b), s);
-        // next group on the side stream
+        cudaEventRecord(ev(b, E_REST), s);
+        // next group's steps
         if (nb_next > 0) {
-            rc = group_panel(c, r0, Wb[(b + 1) & 1], strideW, B);
+            rc = run_group(b + 1, r0, Wb[(b + 1) & 1], nb_next > head0);
             if (rc) return rc;
-            cudaEventRecord(evPanel(b + 1), B);
         }
     }
     // join
     if (cudaEventRecord(la->ev[1], B) != cudaSuccess || cudaStreamWaitEvent(s, la->ev[1], 0) != cudaSuccess)
+        return GPMP_ERR_CUDA;
+    if (cudaEventRecord(la->ev[2], H) != cudaSuccess || cudaStreamWaitEvent(s, la->ev[2], 0) != cudaSuccess)
         return GPMP_ERR_CUDA;
     return block_inverses(c, Wb[0], strideW, s);
 }

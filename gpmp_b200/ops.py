@@ -397,6 +397,15 @@ def lik_grad(state, want_dz, want_dK):
     return g, dz, dK
 
 
+def lik_loo(state, z):
+    """(zloo, sigma2loo, eloo) device vectors from a fitted state (workspace sized for the gradient)."""
+    n = state.n
+    zloo, s2, e = _empty((n,)), _empty((n,)), _empty((n,))
+    check(lib().gpmp_lik_loo(n, state.q, ptr(state.work), state.work.numel(), ptr(z), ptr(zloo), ptr(s2), ptr(e),
+                             stream_ptr()), "gpmp_lik_loo")
+    return zloo, s2, e
+
+
 def _scalar_like(param, value):
     t = torch.tensor(value, dtype=F64)
     if torch.is_tensor(param) and param.device.type != "cpu":
@@ -503,9 +512,20 @@ def predict_chunk(state, xt, Pt, ktt, Vt, want_lambda):
 # --------------------------------------------------------------------------------------------------
 # batched criterion
 # --------------------------------------------------------------------------------------------------
-def criterion_batched(theta, x, z, P, p, noise=False, max_bytes=None):
+def criterion_batched_workspace(n, q, N, max_bytes=None):
+    """Workspace tensor for up to N particles in flight (capped at max_bytes, default 16 GiB)."""
+    if max_bytes is None:
+        max_bytes = 16 << 30
+    per1 = lib().gpmp_criterion_batched_bytes(n, q, 1)
+    per2 = lib().gpmp_criterion_batched_bytes(n, q, 2) - per1
+    nb = max(1, min(max(N, 1), (max_bytes - per1) // max(per2, 1) + 1))
+    return _workspace(lib().gpmp_criterion_batched_bytes(n, q, int(nb)))
+
+
+def criterion_batched(theta, x, z, P, p, noise=False, max_bytes=None, work=None):
     """N criterion values at the rows of theta (N x (1+noise+d)) on fixed (x, z, P); device tensors in,
-    (values[N], info[N]) device tensors out."""
+    (values[N], info[N]) device tensors out.  `work` (optional) is a reusable workspace from
+    criterion_batched_workspace; it decides how many particles are in flight per chunk."""
     N = theta.shape[0]
     n, d = x.shape
     q = 0 if P is None else P.shape[1]
@@ -514,13 +534,8 @@ def criterion_batched(theta, x, z, P, p, noise=False, max_bytes=None):
     info = torch.empty(max(N, 1), dtype=torch.int32, device=device())
     if N == 0:
         return values, info[:0]
-    if max_bytes is None:
-        free, _ = torch.cuda.mem_get_info()
-        max_bytes = min(int(free * 0.6), 48 << 30)
-    per1 = lib().gpmp_criterion_batched_bytes(n, q, 1)
-    per2 = lib().gpmp_criterion_batched_bytes(n, q, 2) - per1
-    nb = max(1, min(N, (max_bytes - per1) // max(per2, 1) + 1))
-    work = _workspace(lib().gpmp_criterion_batched_bytes(n, q, int(nb)))
+    if work is None:
+        work = criterion_batched_workspace(n, q, N, max_bytes)
     check(lib().gpmp_criterion_batched(C.byref(spec), ptr(theta), N, ptr(x), n, ptr(z), ptr(P), q, ptr(work),
                                        work.numel(), ptr(values), ptr(info), stream_ptr()),
           "gpmp_criterion_batched")

@@ -167,6 +167,13 @@ int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, 
                   size_t work_bytes, double* grad_dev, double* dz_dev, double* dK_dev, long long lddk,
                   void* stream);
 
+/* Leave-one-out predictions by virtual cross-validation (replaces gpmp/core/loo.py:65-130 behind Model.loo,
+ * gpmp/core/model.py:309-343) after gpmp_lik_value on a workspace sized with want_grad = 1 and the (centred)
+ * data z_dev that was whitened:  eloo_i = (Pi z)_i / Pi_ii,  s2loo_i = 1 / Pi_ii,  zloo_i = z_i - eloo_i, with
+ * Pi = K^-1 - K^-1 P (P^T K^-1 P)^-1 P^T K^-1 (= K^-1 when q == 0). */
+int gpmp_lik_loo(int n, int q, void* work_dev, size_t work_bytes, const double* z_dev, double* zloo_dev,
+                 double* s2loo_dev, double* eloo_dev, void* stream);
+
 /* ---- L2: kriging prediction (replaces gpmp/core/kriging.py:35-116,170-199 behind Model.predict,
  * gpmp/core/model.py:227-307) for one chunk of m test points, after gpmp_lik_value on work_dev (the
  * fitted state: L, whitened data, Q~, R~).

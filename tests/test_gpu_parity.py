@@ -222,6 +222,17 @@ def test_likelihoods_and_gradients(gp, golden_np, golden_t, case):
         assert relerr_norm(g.numpy(), gt["nll_param_grad"]) <= TOL_LIK
 
 
+@pytest.mark.parametrize("case", [c[0] for c in cases.LIK_CASES])
+def test_loo(gp, golden_np, case):
+    name, n, d, p, kind, noise, seed = next(c for c in cases.LIK_CASES if c[0] == case)
+    g = golden_np(case)
+    m = _model(gp, kind, p, noise, g["theta"])
+    zloo, s2, e = m.loo(g["x"], g["z"], convert_out=True)
+    assert relerr_norm(zloo, g["loo_z"]) <= 1e-7
+    assert relerr_norm(s2, g["loo_s2"]) <= 1e-7
+    assert relerr_norm(e, g["loo_e"]) <= 1e-7
+
+
 def test_likelihood_not_pd_gives_inf(gp):
     x = np.random.default_rng(0).uniform(size=(40, 2))
     z = np.arange(40.0)
