@@ -67,6 +67,12 @@ SIGNATURES = {
     "gpmp_lik_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gpmp_lik_value": (_i, [_specp, _vp, _ll, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp]),
     "gpmp_lik_grad": (_i, [_specp, _vp, _i, _i, _vp, _sz, _vp, _vp, _vp, _ll, _vp]),
+    "gpmp_lik_dist_block": (_i, [_i]),
+    "gpmp_lik_dist_prepare": (_i, [_specp, _vp, _ll, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "gpmp_lik_dist_group": (_i, [_i, _i, _vp, _sz, _i, _vp, _vp, _vp]),
+    "gpmp_lik_dist_store": (_i, [_i, _i, _vp, _sz, _i, _vp, _vp]),
+    "gpmp_lik_dist_update": (_i, [_i, _i, _vp, _sz, _i, _vp, _i, _i, _vp]),
+    "gpmp_lik_dist_finish": (_i, [_i, _i, _vp, _sz, _vp, _vp, _vp]),
     "gpmp_lik_loo": (_i, [_i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "gpmp_predict_scratch_bytes": (_sz, [_i, _i, _i]),
     "gpmp_predict_chunk": (_i, [_specp, _vp, _i, _i, _vp, _sz, _vp, _i, _vp, _vp, _vp, _ll, _vp, _sz, _vp, _vp,

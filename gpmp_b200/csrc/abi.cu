@@ -262,18 +262,9 @@ size_t gpmp_lik_workspace_bytes(int n, int q, int d, int want_grad) {
     return want_grad ? w.total_grad : w.total_value;
 }
 
-int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk, const double* x_dev, int n,
-                   const double* z_dev, const double* P_dev, int q, void* work_dev, size_t work_bytes,
-                   double* out_dev, int* info_dev, void* stream) {
-    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !z_dev || !work_dev || !out_dev || !info_dev) return GPMP_ERR_ARG;
-    if (q > 0 && !P_dev) return GPMP_ERR_ARG;
-    if (!spec && !K_dev) return GPMP_ERR_ARG;
-    if (spec && !x_dev) return GPMP_ERR_ARG;
-    if (!aligned16(work_dev)) return GPMP_ERR_ALIGN;
-    cudaStream_t s = (cudaStream_t)stream;
-    LikWs w = lik_ws(n, q, spec ? spec->d : 1);
-    if (work_bytes < w.total_value) return GPMP_ERR_WORKSPACE;
-    char* base = static_cast<char*>(work_dev);
+static int lik_prepare(const gpmp_cov_spec* spec, const double* K_dev, long long ldk, const double* x_dev, int n,
+                       const double* z_dev, const double* P_dev, int q, const LikWs& w, char* base, int* info_dev,
+                       cudaStream_t s) {
     double* A = (double*)(base + w.off_A);
     int rc;
     if (cudaMemsetAsync(info_dev, 0, sizeof(int), s) != cudaSuccess) return GPMP_ERR_CUDA;
@@ -284,14 +275,13 @@ int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk
     lr.P = P_dev; lr.z = z_dev; lr.n = n; lr.q = q;
     lr.rows = A + (long long)n * w.lda; lr.ld = w.lda; lr.stride = 0;
     lr.p0rows = q > 0 ? (double*)(base + w.off_p0rows) : nullptr; lr.ld0 = w.lda;
-    rc = launch_load_rows(lr, 1, s);
-    if (rc) return rc;
-    char* pb = base + w.off_potrf;
-    rc = potrf_core(A, w.lda, 0, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo), (double*)(pb + w.pw.off_tup), 0,
-                    (double*)(pb + w.pw.off_w), 0, info_dev, 0, 1, s);
-    if (rc) return rc;
+    return launch_load_rows(lr, 1, s);
+}
+
+static int lik_finalize(int n, int q, const LikWs& w, char* base, double* out_dev, int* info_dev, cudaStream_t s) {
+    double* A = (double*)(base + w.off_A);
     FinalizeArgs f;
-    f.rows = lr.rows; f.ld = w.lda; f.strideRows = 0;
+    f.rows = A + (long long)n * w.lda; f.ld = w.lda; f.strideRows = 0;
     f.p0rows = (double*)(base + w.off_p0rows); f.ld0 = w.lda;
     f.p0work = (double*)(base + w.off_p0work); f.strideP0 = 0;
     f.Ldiag = A; f.ldl = w.lda; f.strideL = 0;
@@ -301,6 +291,96 @@ int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk
     f.info = info_dev; f.strideInfo = 0;
     f.ldr0_in = nullptr;
     return launch_finalize(f, 1, s);
+}
+
+static int lik_check(const gpmp_cov_spec* spec, const double* K_dev, const double* x_dev, int n, const double* z_dev,
+                     const double* P_dev, int q, const void* work_dev) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !z_dev || !work_dev) return GPMP_ERR_ARG;
+    if (q > 0 && !P_dev) return GPMP_ERR_ARG;
+    if (!spec && !K_dev) return GPMP_ERR_ARG;
+    if (spec && !x_dev) return GPMP_ERR_ARG;
+    if (!aligned16(work_dev)) return GPMP_ERR_ALIGN;
+    return GPMP_OK;
+}
+
+int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk, const double* x_dev, int n,
+                   const double* z_dev, const double* P_dev, int q, void* work_dev, size_t work_bytes,
+                   double* out_dev, int* info_dev, void* stream) {
+    int rc = lik_check(spec, K_dev, x_dev, n, z_dev, P_dev, q, work_dev);
+    if (rc) return rc;
+    if (!out_dev || !info_dev) return GPMP_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    LikWs w = lik_ws(n, q, spec ? spec->d : 1);
+    if (work_bytes < w.total_value) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    rc = lik_prepare(spec, K_dev, ldk, x_dev, n, z_dev, P_dev, q, w, base, info_dev, s);
+    if (rc) return rc;
+    char* pb = base + w.off_potrf;
+    rc = potrf_core((double*)(base + w.off_A), w.lda, 0, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo),
+                    (double*)(pb + w.pw.off_tup), 0, (double*)(pb + w.pw.off_w), 0, info_dev, 0, 1, s);
+    if (rc) return rc;
+    return lik_finalize(n, q, w, base, out_dev, info_dev, s);
+}
+
+// ---- the same evaluation with the factorisation partitioned over GPUs (panel exchange by the caller) -----
+int gpmp_lik_dist_block(int n) { return potrf_block_size(n); }
+
+int gpmp_lik_dist_prepare(const gpmp_cov_spec* spec, const double* K_dev, long long ldk, const double* x_dev, int n,
+                          const double* z_dev, const double* P_dev, int q, void* work_dev, size_t work_bytes,
+                          int* info_dev, void* stream) {
+    int rc = lik_check(spec, K_dev, x_dev, n, z_dev, P_dev, q, work_dev);
+    if (rc) return rc;
+    if (!info_dev) return GPMP_ERR_ARG;
+    LikWs w = lik_ws(n, q, spec ? spec->d : 1);
+    if (work_bytes < w.total_value) return GPMP_ERR_WORKSPACE;
+    return lik_prepare(spec, K_dev, ldk, x_dev, n, z_dev, P_dev, q, w, static_cast<char*>(work_dev), info_dev,
+                       (cudaStream_t)stream);
+}
+
+int gpmp_lik_dist_group(int n, int q, void* work_dev, size_t work_bytes, int k0, double* panel_dev, int* info_dev,
+                        void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !panel_dev || !info_dev || k0 < 0 || k0 >= n)
+        return GPMP_ERR_ARG;
+    LikWs w = lik_ws(n, q, 1);
+    if (work_bytes < w.total_value || (k0 % w.pw.NB) != 0) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    char* pb = base + w.off_potrf;
+    return dist_group((double*)(base + w.off_A), w.lda, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo),
+                      (double*)(pb + w.pw.off_tup), k0, panel_dev, info_dev, (cudaStream_t)stream);
+}
+
+int gpmp_lik_dist_store(int n, int q, void* work_dev, size_t work_bytes, int k0, const double* panel_dev,
+                        void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !panel_dev || k0 < 0 || k0 >= n) return GPMP_ERR_ARG;
+    LikWs w = lik_ws(n, q, 1);
+    if (work_bytes < w.total_value || (k0 % w.pw.NB) != 0) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    return dist_store((double*)(base + w.off_A), w.lda, n, w.nrows, w.pw.NB, k0, panel_dev, (cudaStream_t)stream);
+}
+
+int gpmp_lik_dist_update(int n, int q, void* work_dev, size_t work_bytes, int k0, const double* panel_dev, int col0,
+                         int col1, void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !panel_dev || k0 < 0 || k0 >= n) return GPMP_ERR_ARG;
+    LikWs w = lik_ws(n, q, 1);
+    if (work_bytes < w.total_value || (k0 % w.pw.NB) != 0) return GPMP_ERR_WORKSPACE;
+    if (col1 > n) col1 = n;
+    char* base = static_cast<char*>(work_dev);
+    return dist_update((double*)(base + w.off_A), w.lda, n, w.nrows, w.pw.NB, k0, panel_dev, col0, col1,
+                       (cudaStream_t)stream);
+}
+
+int gpmp_lik_dist_finish(int n, int q, void* work_dev, size_t work_bytes, double* out_dev, int* info_dev,
+                         void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !out_dev || !info_dev) return GPMP_ERR_ARG;
+    LikWs w = lik_ws(n, q, 1);
+    if (work_bytes < w.total_value) return GPMP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* base = static_cast<char*>(work_dev);
+    char* pb = base + w.off_potrf;
+    int rc = dist_finish((double*)(base + w.off_A), w.lda, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo),
+                         (double*)(pb + w.pw.off_tup), (double*)(pb + w.pw.off_w), info_dev, s);
+    if (rc) return rc;
+    return lik_finalize(n, q, w, base, out_dev, info_dev, s);
 }
 
 int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, void* work_dev, size_t work_bytes,

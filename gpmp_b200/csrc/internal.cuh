@@ -40,6 +40,13 @@ int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,
                    double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream);
 
+int dist_group(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, int k0, double* panel,
+               int* info, cudaStream_t stream);
+int dist_store(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, cudaStream_t stream);
+int dist_update(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, int col0, int col1,
+                cudaStream_t stream);
+int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, double* scratch,
+                int* info, cudaStream_t stream);
 int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int* info, long long* dbg,
                 cudaStream_t stream);
 

@@ -32,6 +32,7 @@ struct Potf2Args {
     int* info; long long strideInfo;
     int row0;          // global index of the tile's first row (for info)
     long long* dbg;    // optional: clock64() at the phase boundaries (development only)
+    int invert_only;   // the tile already holds L (received from another rank): skip the factorisation
 };
 #define POTF2_STAMP(i)                                              \
     do {                                                            \
@@ -132,7 +133,11 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
 
     POTF2_STAMP(1);
     int bad = 0;  // 1-based local index of the first non-positive pivot (warp 0, lane 0 only)
-    for (int jb = 0; jb < 4; ++jb) {
+    if (a.invert_only) {
+        if (tid < PT) rinv[tid] = 1.0 / S[tid * PLD + tid];
+        __syncthreads();
+    }
+    for (int jb = 0; jb < (a.invert_only ? 0 : 4); ++jb) {
         const int c0 = jb * 32;
         POTF2_STAMP(2 + 3 * jb);
         if (warp == 0) {
@@ -417,7 +422,7 @@ int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int*
                 cudaStream_t stream) {
     Potf2Args pa;
     pa.A = A; pa.lda = lda; pa.strideA = 0; pa.Tlo = Tlo; pa.Tup = Tup; pa.ldt = PT; pa.strideT = 0; pa.nb = nb;
-    pa.info = info; pa.strideInfo = 0; pa.row0 = 0; pa.dbg = dbg;
+    pa.info = info; pa.strideInfo = 0; pa.row0 = 0; pa.dbg = dbg; pa.invert_only = 0;
     return launch_potf2(pa, 1, stream);
 }
 
@@ -531,7 +536,7 @@ static int tile_step(const PotrfCtx& c, int k0, int j0, double* Wg, long long st
     pa.A = c.A + (long long)col * (lda + 1); pa.lda = lda; pa.strideA = c.strideA;
     pa.Tlo = Tlo_k + (long long)j0 * (NB + 1); pa.Tup = Tup_k + (long long)j0 * (NB + 1);
     pa.ldt = NB; pa.strideT = c.strideT; pa.nb = jb; pa.info = c.info; pa.strideInfo = c.strideInfo;
-    pa.row0 = col; pa.dbg = nullptr;
+    pa.row0 = col; pa.dbg = nullptr; pa.invert_only = 0;
     int rc = launch_potf2(pa, c.batch, stream);
     if (rc) return rc;
     const int M = c.nrows - rb;
@@ -768,6 +773,100 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
     if (cudaEventRecord(la->ev[2], H) != cudaSuccess || cudaStreamWaitEvent(s, la->ev[2], 0) != cudaSuccess)
         return GPMP_ERR_CUDA;
     return block_inverses(c, Wb[0], strideW, s);
+}
+
+// ---- panel-partitioned factorisation across GPUs ------------------------------------------------------
+// One process per GPU holds the whole work matrix but only keeps its own column groups (group g belongs to
+// rank g mod G) up to date.  The owner factors a group into the panel buffer, the caller broadcasts the
+// buffer (NCCL), every rank applies the panel to the column groups it owns, non-owners also file the panel
+// into their copy of L.  The pieces below are what the C-ABI exposes for that loop.
+struct Copy2DArgs { const double* src; long long lds; double* dst; long long ldd; int rows, cols; };
+__global__ void copy2d_kernel(const Copy2DArgs a) {
+    const int r = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.cols; c += gridDim.x * blockDim.x)
+        a.dst[(long long)r * a.ldd + c] = a.src[(long long)r * a.lds + c];
+}
+static int launch_copy2d(const double* src, long long lds, double* dst, long long ldd, int rows, int cols,
+                         cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return GPMP_OK;
+    Copy2DArgs a{src, lds, dst, ldd, rows, cols};
+    LaunchScope scope(KC_SMALL, 0.0, stream);
+    dim3 grid(ceil_div(cols, 128), rows);
+    copy2d_kernel<<<grid, 128, 0, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
+// Owner: factor the group at k0 (its columns carry every earlier update) and leave in `panel` (ld NB) the
+// group's block column of L: row (r - k0) = L[r][k0 .. k0+gw) for r = k0 .. nrows-1 (diagonal tiles included).
+int dist_group(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, int k0, double* panel,
+               int* info, cudaStream_t stream) {
+    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1};
+    int rc = group_panel(c, k0, panel, 0, stream);
+    if (rc) return rc;
+    const int gw = min(NB, n - k0);
+    for (int j0 = 0; j0 < gw; j0 += PT) {
+        const int jb = min(PT, gw - j0), col = k0 + j0;
+        rc = launch_copy2d(A + (long long)col * (lda + 1), lda, panel + (long long)j0 * NB + j0, NB, jb, jb, stream);
+        if (rc) return rc;
+    }
+    return GPMP_OK;
+}
+
+// Non-owner: file a received panel into A (diagonal tiles, rows below each tile, mirrored upper tiles).
+int dist_store(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, cudaStream_t stream) {
+    const int gw = min(NB, n - k0);
+    for (int j0 = 0; j0 < gw; j0 += PT) {
+        const int jb = min(PT, gw - j0), col = k0 + j0, rb = col + jb;
+        int rc = launch_copy2d(panel + (long long)j0 * NB + j0, NB, A + (long long)col * (lda + 1), lda, jb, jb, stream);
+        if (rc) return rc;
+        const int M = nrows - rb;
+        if (M <= 0) continue;
+        CopyPanelArgs cp;
+        cp.W = panel + (long long)(rb - k0) * NB + j0; cp.ldw = NB; cp.strideW = 0;
+        cp.Alo = A + (long long)rb * lda + col; cp.Aup = A + (long long)col * lda + rb;
+        cp.lda = lda; cp.strideA = 0; cp.rows = M; cp.cols = jb; cp.mirror_rows = max(0, n - rb);
+        rc = launch_copy_panel(cp, 1, stream);
+        if (rc) return rc;
+    }
+    return GPMP_OK;
+}
+
+// Every rank: trailing update of the absolute columns [col0, col1) (beyond the group at k0) with its panel.
+int dist_update(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, int col0, int col1,
+                cudaStream_t stream) {
+    PotrfCtx c{A, lda, 0, n, nrows, NB, nullptr, nullptr, 0, nullptr, 0, 1};
+    const int gw = min(NB, n - k0), r0 = k0 + gw;
+    if (col0 < r0 || col1 <= col0) return GPMP_ERR_ARG;
+    return trailing_update(c, k0, panel + (long long)gw * NB, NB, 0, col0 - r0, col1 - r0, stream);
+}
+
+// Every rank, after the last panel: tile inverses from the (received) factor, then the NB-wide inverses.
+int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, double* scratch,
+                int* info, cudaStream_t stream) {
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int gw = min(NB, n - k0);
+        double* Tlo_k = Tlo + (long long)(k0 / NB) * NB * NB;
+        double* Tup_k = Tup + (long long)(k0 / NB) * NB * NB;
+        const int full = gw / PT, rem = gw - full * PT;
+        Potf2Args pa;
+        pa.A = A + (long long)k0 * (lda + 1); pa.lda = lda; pa.strideA = (long long)PT * (lda + 1);
+        pa.Tlo = Tlo_k; pa.Tup = Tup_k; pa.ldt = NB; pa.strideT = (long long)PT * (NB + 1);
+        pa.nb = PT; pa.info = nullptr; pa.strideInfo = 0; pa.row0 = k0; pa.dbg = nullptr; pa.invert_only = 1;
+        int rc;
+        if (full > 0) {
+            rc = launch_potf2(pa, full, stream);
+            if (rc) return rc;
+        }
+        if (rem > 0) {
+            pa.A += (long long)full * pa.strideA; pa.Tlo += (long long)full * pa.strideT;
+            pa.Tup += (long long)full * pa.strideT; pa.nb = rem;
+            rc = launch_potf2(pa, 1, stream);
+            if (rc) return rc;
+        }
+    }
+    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1};
+    return block_inverses(c, scratch, 0, stream);
 }
 
 // ---- potri: Tlo/Tup (n x n) from L and the compact NB-block inverses, then Kinv = T^T T (lower) ----

@@ -44,3 +44,41 @@ def all_gather_rows(local, N, group=None):
         lo, hi = block_bounds(N, r, size)
         chunks.append(parts[r][: hi - lo])
     return torch.cat(chunks)
+
+
+def reml_value_distributed(model, covparam, xi, zi, group=None):
+    """Model.negative_log_restricted_likelihood (value only) with the Cholesky factorisation partitioned over
+    the ranks of `group` (BASELINE config 5a).  Returns (value, FitState); every rank gets the same value and
+    a complete fitted state (so prediction chunks can be sharded over ranks afterwards)."""
+    from . import core, kernel, num, ops
+
+    xi_, zi_, _ = core._ensure_shapes_and_type(xi=xi, zi=zi)
+    P = model._basis(xi_) if model.meantype == "linear_predictor" else None
+    if model.meantype == "parameterized":
+        zi_ = zi_ - ops.to_device(model.mean(xi_, num.asparam(model.meanparam))).reshape(-1)
+    K, fused = model._same_set_cov(xi_, num.asparam(covparam))
+    with torch.no_grad():
+        if fused:
+            spec = ops._spec_from_param(K.p, xi_.shape[1], ops.host_values(K.param))
+            state, out = ops.lik_value_dist(spec, None, xi_, zi_, P, group)
+        else:
+            Kd = kernel.materialize(K).detach().contiguous()
+            state, out = ops.lik_value_dist(None, Kd, None, zi_, P, group)
+    return ops.read_small(out)[0], state
+
+
+def predict_distributed(model, xi, zi, xt, group=None, convert_out=True):
+    """Model.predict with the test points block-partitioned over the ranks of `group` (independent columns,
+    SURVEY.md 8e): every rank fits (xi, zi) -- replicated, or use reml_value_distributed first for one large
+    factorisation -- predicts its block of xt and the (mean, variance) vectors are all-gathered."""
+    from . import num
+
+    rank, size = world(group)
+    m = xt.shape[0]
+    lo, hi = block_bounds(m, rank, size)
+    mean, var = model.predict(xi, zi, xt[lo:hi], convert_out=False)
+    mean = all_gather_rows(mean, m, group)
+    var = all_gather_rows(var, m, group)
+    if convert_out:
+        return num.to_np(mean), num.to_np(var)
+    return mean, var

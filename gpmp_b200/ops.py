@@ -384,6 +384,74 @@ def lik_value(spec, K, x, z, P, want_grad):
     return FitState(work, n, q, d, spec, x, want_grad), out
 
 
+def lik_value_dist(spec, K, x, z, P, group=None):
+    """lik_value with the factorisation partitioned over the ranks of `group` (one process per GPU): column
+    groups are owned round-robin, the owner factors a group, the panel is broadcast with NCCL, every rank
+    updates the groups it owns.  Every rank ends with the same FitState a local lik_value would leave."""
+    import torch.distributed as td
+
+    from . import dist as gdist
+
+    rank, size = gdist.world(group)
+    n = z.shape[0]
+    q = 0 if P is None else P.shape[1]
+    d = x.shape[1] if x is not None else 1
+    work = _workspace(lib().gpmp_lik_workspace_bytes(n, q, d, 0))
+    out = _empty((8,))
+    info = torch.empty(1, dtype=torch.int32, device=device())
+    specp = C.byref(spec) if spec is not None else None
+    check(lib().gpmp_lik_dist_prepare(specp, ptr(K), _ld(K) if K is not None else 0, ptr(x), n, ptr(z), ptr(P), q,
+                                      ptr(work), work.numel(), ptr(info), stream_ptr()), "gpmp_lik_dist_prepare")
+    NB = lib().gpmp_lik_dist_block(n)
+    nrows = n + q + 1
+    ngroups = (n + NB - 1) // NB
+    bufs = [_empty((nrows * NB,)), _empty((nrows * NB,))]
+    wb = work.numel()
+    def root(g):
+        owner = g % size
+        return td.get_global_rank(group, owner) if group is not None else owner
+
+    def bcast(g):
+        if size == 1:
+            return None
+        return td.broadcast(bufs[g & 1][: (nrows - g * NB) * NB], src=root(g), group=group, async_op=True)
+
+    def update(g, g2):
+        check(lib().gpmp_lik_dist_update(n, q, ptr(work), wb, g * NB, ptr(bufs[g & 1]), g2 * NB,
+                                         min(n, (g2 + 1) * NB), stream_ptr()), "gpmp_lik_dist_update")
+
+    def factor(g):
+        check(lib().gpmp_lik_dist_group(n, q, ptr(work), wb, g * NB, ptr(bufs[g & 1]), ptr(info), stream_ptr()),
+              "gpmp_lik_dist_group")
+
+    if rank == 0 % size:
+        factor(0)
+    pending = bcast(0)
+    for g in range(ngroups):
+        if pending is not None:
+            pending.wait()  # panel g has arrived (the compute stream now waits for it)
+        if size > 1 and rank != g % size:
+            check(lib().gpmp_lik_dist_store(n, q, ptr(work), wb, g * NB, ptr(bufs[g & 1]), stream_ptr()),
+                  "gpmp_lik_dist_store")
+        nxt = g + 1
+        if nxt < ngroups:
+            # the chain first: the owner of the next group brings it up to date, factors it and starts the
+            # broadcast; everybody else posts the receive into the other buffer and keeps updating
+            if rank == nxt % size:
+                update(g, nxt)
+                factor(nxt)
+            pending = bcast(nxt)
+        for g2 in range(g + 2, ngroups):
+            if g2 % size == rank:
+                update(g, g2)
+    if size > 1:
+        # a non-positive pivot is seen by the owner of its group only
+        td.all_reduce(info, op=td.ReduceOp.MAX, group=group)
+    check(lib().gpmp_lik_dist_finish(n, q, ptr(work), wb, ptr(out), ptr(info), stream_ptr()),
+          "gpmp_lik_dist_finish")
+    return FitState(work, n, q, d, spec, x, False), out
+
+
 def lik_grad(state, want_dz, want_dK):
     n, q, d = state.n, state.q, state.d
     spec = state.spec

@@ -167,6 +167,28 @@ int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, 
                   size_t work_bytes, double* grad_dev, double* dz_dev, double* dK_dev, long long lddk,
                   void* stream);
 
+/* The same evaluation with the factorisation partitioned over the GPUs of one node (one process per GPU,
+ * SURVEY.md 8e "one large Cholesky"): column groups of gpmp_lik_dist_block(n) columns, group g owned by rank
+ * g mod G.  Every rank holds a full workspace (gpmp_lik_workspace_bytes) but keeps only its own groups up to
+ * date.  Per group, in order:  owner: gpmp_lik_dist_group (factor the group, fill panel_dev with the group's
+ * block column of L: (n+q+1-k0) x block doubles, ld = block);  caller: broadcast panel_dev (ncclBroadcast /
+ * torch.distributed.broadcast);  non-owners: gpmp_lik_dist_store (file the panel into their L);  every rank:
+ * gpmp_lik_dist_update for each later group it owns (columns [col0, col1)).  After the last group
+ * gpmp_lik_dist_finish leaves on every rank exactly the state gpmp_lik_value leaves (out_dev as there), so
+ * gpmp_predict_chunk / gpmp_lik_grad / gpmp_lik_loo can follow. */
+int gpmp_lik_dist_block(int n);
+int gpmp_lik_dist_prepare(const gpmp_cov_spec* spec, const double* K_dev, long long ldk, const double* x_dev,
+                          int n, const double* z_dev, const double* P_dev, int q, void* work_dev,
+                          size_t work_bytes, int* info_dev, void* stream);
+int gpmp_lik_dist_group(int n, int q, void* work_dev, size_t work_bytes, int k0, double* panel_dev,
+                        int* info_dev, void* stream);
+int gpmp_lik_dist_store(int n, int q, void* work_dev, size_t work_bytes, int k0, const double* panel_dev,
+                        void* stream);
+int gpmp_lik_dist_update(int n, int q, void* work_dev, size_t work_bytes, int k0, const double* panel_dev,
+                         int col0, int col1, void* stream);
+int gpmp_lik_dist_finish(int n, int q, void* work_dev, size_t work_bytes, double* out_dev, int* info_dev,
+                         void* stream);
+
 /* Leave-one-out predictions by virtual cross-validation (replaces gpmp/core/loo.py:65-130 behind Model.loo,
  * gpmp/core/model.py:309-343) after gpmp_lik_value on a workspace sized with want_grad = 1 and the (centred)
  * data z_dev that was whitened:  eloo_i = (Pi z)_i / Pi_ii,  s2loo_i = 1 / Pi_ii,  zloo_i = z_i - eloo_i, with

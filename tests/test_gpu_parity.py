@@ -332,6 +332,25 @@ def test_batched_matches_scalar_path_n512(gp):
     assert relerr(vals[3], ref) <= TOL_LIK
 
 
+def test_partitioned_factorisation_matches_local(gp):
+    """The panel-partitioned evaluation (owner factors a column group, panel exchange, per-rank updates) run
+    with a single rank must reproduce the local pipeline bit for bit, and leave a state predict can use."""
+    n, d = 1500, 5
+    x, z, xt = cases.data(n, d, 31, m=40)
+    th = cases.theta(d, 31)
+    m = _model(gp, "linear", 2, False, th)
+    v_local = m.negative_log_restricted_likelihood(th, x, z).item()
+    v_dist, state = gp.dist.reml_value_distributed(m, th, x, z)
+    assert v_dist == v_local
+    ref = onp.negative_log_restricted_likelihood(
+        onp.OracleModel(cases.mean_fn("linear", np), lambda a, b, cp, pw=False: onp.maternp_covariance(a, b, 2, cp, pw),
+                        None, th, "linear_predictor"), th, x, z)
+    assert relerr(v_dist, ref) <= TOL_LIK
+    mean, var = gp.dist.predict_distributed(m, x, z, xt)
+    mean1, var1 = m.predict(x, z, xt)
+    assert np.array_equal(mean, mean1) and np.array_equal(var, var1)
+
+
 # ----------------------------------------------------------------------------------------------------
 def test_headline_size_properties(gp):
     """n=8192, d=8 (BASELINE config 3): size-independent checks at full size.
