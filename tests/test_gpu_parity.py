@@ -245,6 +245,39 @@ def test_likelihood_not_pd_gives_inf(gp):
     assert torch.isinf(val) and torch.all(grad == 0)
 
 
+def test_reml_selection_example02_end_to_end(gp, golden_t):
+    """BASELINE config 1: the SciPy SLSQP loop of select_parameters_with_reml
+    (kernel/parameter_selection.py:128-276: same start, +-10 box, ftol=1e-6, eps=1e-8, best-seen tracking)
+    driven by this library's criterion and gradient must land on the reference's selected parameters, and
+    predict from there must reproduce its posterior mean / variance."""
+    from scipy.optimize import minimize
+
+    g = golden_t("select_reml_example02")
+    x, z, xt, p, th0 = g["x"], g["z"], g["xt"], int(g["p"]), g["covparam0"]
+    m = gp.core.Model(cases.mean_fn("const", gp.num),
+                      lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, p, cp, pairwise))
+    crit = gp.num.DifferentiableSelectionCriterion(
+        lambda p_, x_, z_: m.negative_log_restricted_likelihood(p_, x_, z_), x, z)
+    best = {"J": np.inf, "p": None}
+
+    def fun(pv):
+        J = crit.evaluate_pre_grad(pv)
+        if J < best["J"]:
+            best["J"], best["p"] = J, pv.copy()
+        return J
+
+    r = minimize(fun, th0, method="SLSQP", jac=lambda pv: np.asarray(crit.gradient(pv)),
+                 bounds=[(v - 10.0, v + 10.0) for v in th0], options=dict(ftol=1e-6, eps=1e-8, maxiter=15000))
+    assert r.success
+    assert abs(best["J"] - float(g["fun"])) <= 1e-6 * max(1.0, abs(float(g["fun"])))
+    assert np.max(np.abs(best["p"] - g["covparam"])) <= 1e-3
+    m.covparam = g["covparam"]  # predict at the reference's parameters: isolates the predictor from the optimiser
+    mean, var = m.predict(x, z, xt)
+    s2 = float(np.exp(g["covparam"][0]))
+    assert np.max(np.abs(mean - g["mean"])) / max(np.sqrt(s2), np.max(np.abs(g["mean"]))) <= 1e-8
+    assert np.max(np.abs(var - g["var"])) / s2 <= 1e-8
+
+
 def test_selection_criterion_lifecycle(gp, golden_np, golden_t):
     """evaluate_pre_grad / gradient / evaluate_no_grad as SciPy drives them (torch_backend.py:547-604)."""
     case = "lik_n500_d8_p2_const"
@@ -330,6 +363,48 @@ def test_batched_matches_scalar_path_n512(gp):
         onp.OracleModel(cases.mean_fn("const", np), lambda a, b, cp, pw=False: onp.maternp_covariance(a, b, 2, cp, pw),
                         None, th0, "linear_predictor"), TH[3], x, z)
     assert relerr(vals[3], ref) <= TOL_LIK
+
+
+def test_edge_shapes_and_inputs(gp):
+    """Edge cases the reference's call conventions allow: a (n,1) column for zi, NumPy covparam, a wide
+    linear basis (q = d + 1 = 11), d = 32, n = 1, empty prediction sets."""
+    rng = np.random.default_rng(11)
+    # q = 11, d = 10, value + gradient against the oracle (analytic form checked against reference autograd)
+    n, d = 260, 10
+    x, z, xt = cases.data(n, d, 12, m=33)
+    th = cases.theta(d, 12)
+    m = _model(gp, "linear", 2, False, th)
+    tp = torch.tensor(th, requires_grad=True)
+    v = m.negative_log_restricted_likelihood(tp, x, z.reshape(-1, 1))
+    (g,) = torch.autograd.grad(v, tp)
+    P = np.hstack((np.ones((n, 1)), x))
+    vr, gr = onp.reml_value_and_grad_analytic(x, z, P, 2, th)
+    assert relerr(v.item(), vr) <= TOL_LIK and relerr_norm(g.numpy(), gr) <= TOL_LIK
+    om = onp.OracleModel(cases.mean_fn("linear", np), lambda a, b, cp, pw=False: onp.maternp_covariance(a, b, 2, cp, pw),
+                         None, th, "linear_predictor")
+    mu_r, var_r = onp.predict(om, x, z, xt)[:2]
+    mu, var = m.predict(x, z, xt)
+    s2 = float(np.exp(th[0]))
+    assert np.max(np.abs(mu - mu_r)) / max(np.sqrt(s2), np.max(np.abs(mu_r))) <= 1e-8
+    assert np.max(np.abs(var - var_r)) / s2 <= 1e-8
+    mu0, var0 = m.predict(x, z, xt[:0])
+    assert mu0.shape == (0,) and var0.shape == (0,)
+    # d = 32 covariance
+    x32 = rng.uniform(size=(70, 32))
+    th32 = np.concatenate(([0.2], rng.normal(size=32) * 0.3 - 1.0))
+    K = gp.kernel.maternp_covariance(gp.num.asarray(x32), None, 3, th32).cpu().numpy()
+    assert relerr(K, onp.maternp_covariance(x32, x32, 3, th32)) <= TOL_COV
+    with pytest.raises(gp._abi.GpmpError):
+        gp.kernel.maternp_covariance(gp.num.asarray(rng.uniform(size=(5, 33))), None, 2, np.zeros(34))
+    # n = 1 and n = 2
+    for nn in (1, 2):
+        xs, zs = rng.uniform(size=(nn, 2)), rng.normal(size=nn)
+        ths = np.array([0.1, 0.3, -0.2])
+        mz = _model(gp, "zero", 1, False, ths)
+        ref = onp.negative_log_likelihood_zero_mean(
+            onp.OracleModel(None, lambda a, b, cp, pw=False: onp.maternp_covariance(a, b, 1, cp, pw), None, ths, "zero"),
+            ths, xs, zs)
+        assert relerr(mz.negative_log_likelihood_zero_mean(ths, xs, zs).item(), ref) <= TOL_LIK
 
 
 def test_partitioned_factorisation_matches_local(gp):
