@@ -68,6 +68,50 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// 1/sqrt(a) in double: the hardware seed rsqrt.approx.ftz.f64 (MUFU.RSQ64H, ~2^-23 relative, full double
+// range) and two Newton steps -- branch-free, ~10 instructions (the library rsqrt()/sqrt() are long
+// software sequences with slow paths).
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+// sqrt(a) for a >= 0 to ~2 ulp (a * rsqrt(a)); exact zero preserved, NaN / negative give NaN
+__device__ __forceinline__ double fast_sqrt(double a) {
+    const double r = a * fast_rsqrt(a);
+    return a == 0.0 ? 0.0 : r;
+}
+
+// exp(-t) for t >= 0 to ~2 ulp with a short straight-line sequence: k = round(t log2 e), r = k ln2 - t in
+// [-0.347, 0.347], degree-12 Taylor polynomial of e^r (remainder 1.7e-16 relative), scaling by 2^-k through
+// the exponent field.  Results below 2^-1021 flush to zero; NaN propagates.  Branch-free (selects only).
+__device__ __forceinline__ double exp_neg(double t) {
+    const double tc = fmin(t, 707.0);
+    const double kf = rint(tc * 1.4426950408889634);
+    double r = fma(kf, 6.93147180369123816490e-01, -tc);
+    r = fma(kf, 1.90821492927058770002e-10, r);
+    double p = 2.08767569878681e-09;
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 0.0001984126984126984);
+    p = fma(p, r, 0.001388888888888889);
+    p = fma(p, r, 0.008333333333333333);
+    p = fma(p, r, 0.041666666666666664);
+    p = fma(p, r, 0.16666666666666666);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kf;
+    double res = p * __longlong_as_double((long long)(1023 - k) << 52);
+    res = t < 707.0 ? res : 0.0;
+    return t != t ? t : res;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -86,6 +86,78 @@ __device__ __forceinline__ double matern_dk_over_h(const MaternDev& m, double h)
 constexpr int CT = 64;          // tile edge
 constexpr int COV_THREADS = 256;
 
+// Kernel constants held in registers.  P >= 0: regularity known at compile time, Horner coefficients in
+// registers and fully unrolled (p = 0..4 cover every example of the reference but one); P == -1: any p up to
+// GPMP_MAX_P, coefficients read from the shared copy of MaternDev.
+template <int P>
+struct MaternRegs {
+    static constexpr int NA = P > 0 ? P : 1, NB_ = P > 1 ? P - 1 : 1;
+    double c, sigma2, dscale;
+    double a[NA], am1[NB_];
+    const MaternDev* sm;
+    int p;
+    __device__ __forceinline__ void init(const MaternDev* m) {
+        sm = m; p = m->p; c = m->c; sigma2 = m->sigma2; dscale = m->dscale;
+        if (P > 0) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) a[i] = m->coef[i];
+        }
+        if (P > 1) {
+#pragma unroll
+            for (int i = 0; i < NB_; ++i) am1[i] = m->coefm1[i];
+        }
+    }
+    // q_p(2t)
+    __device__ __forceinline__ double poly(double u) const {
+        double acc = 0.0;
+        if (P >= 0) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) acc = (acc + a[i]) * u;
+        } else {
+            for (int i = 0; i < p; ++i) acc = (acc + sm->coef[i]) * u;
+        }
+        return 1.0 + acc;
+    }
+    // q_{p-1}(2t)
+    __device__ __forceinline__ double polym1(double u) const {
+        double acc = 0.0;
+        if (P >= 0) {
+#pragma unroll
+            for (int i = 0; i < P - 1; ++i) acc = (acc + am1[i]) * u;
+        } else {
+            for (int i = 0; i < p - 1; ++i) acc = (acc + sm->coefm1[i]) * u;
+        }
+        return 1.0 + acc;
+    }
+    // sigma2 * k_p(h) and, optionally, sigma2 * k_p'(h)/h (p >= 1) or sigma2 * k_0'(h) (p == 0)
+    __device__ __forceinline__ double cov(double h) const {
+        if (isinf(h)) h = GPMP_BIGF;
+        const double t = c * h;
+        return sigma2 * exp_neg(t) * poly(2.0 * t);
+    }
+    __device__ __forceinline__ void cov_and_dk(double h, double& kc, double& dkh) const {
+        if (isinf(h)) h = GPMP_BIGF;
+        const double t = c * h;
+        const double e = sigma2 * exp_neg(t);
+        kc = e * poly(2.0 * t);
+        const bool p0 = P >= 0 ? (P == 0) : (p == 0);
+        dkh = p0 ? dscale * e : dscale * e * polym1(2.0 * t);
+    }
+};
+
+// Stage the parameter record in shared memory (from the per-batch device array or from the kernel
+// parameters) so that every later access is a shared-memory broadcast, not a generic load.
+__device__ __forceinline__ void stage_matern(MaternDev* dst, const MaternDev* src_dev, const MaternDev& src_param) {
+    double* d = reinterpret_cast<double*>(dst);
+    if (src_dev) {
+        const double* s = reinterpret_cast<const double*>(src_dev);
+        for (int e = threadIdx.x; e < (int)(sizeof(MaternDev) / 8); e += blockDim.x) d[e] = s[e];
+    } else if (threadIdx.x == 0) {
+        *dst = src_param;
+    }
+    __syncthreads();
+}
+
 enum CovMode { CM_RECT = COV_RECT, CM_SYM_FULL = COV_SYM_FULL, CM_SYM_LOWER = COV_SYM_LOWER };
 
 struct CovArgs {
@@ -120,17 +192,15 @@ __device__ __forceinline__ void stage_points(double (*s)[CT], const double* __re
     }
 }
 
+template <int P>
 __global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a) {
     __shared__ __align__(16) double xs[GPMP_MAX_DIM][CT];
     __shared__ __align__(16) double ys[GPMP_MAX_DIM][CT];
     __shared__ MaternDev msh;
-    if (a.mdev) {
-        const double* src = reinterpret_cast<const double*>(a.mdev + blockIdx.z);
-        double* dst = reinterpret_cast<double*>(&msh);
-        for (int e = threadIdx.x; e < (int)(sizeof(MaternDev) / 8); e += COV_THREADS) dst[e] = src[e];
-        __syncthreads();
-    }
-    const MaternDev& m = a.mdev ? msh : a.m;
+    stage_matern(&msh, a.mdev ? a.mdev + blockIdx.z : nullptr, a.m);
+    const MaternDev& m = msh;
+    MaternRegs<P> mr;
+    mr.init(&msh);
     double* __restrict__ Kb = a.K + (long long)blockIdx.z * a.strideK;
     int ti, tj;
     if (a.mode == CM_RECT) {
@@ -170,32 +240,45 @@ __global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double h = sqrt(h2[i][k]);
-            v[i][k] = a.dist_only ? h : m.sigma2 * matern_k(m, h);
+            const double h = fast_sqrt(h2[i][k]);
+            v[i][k] = a.dist_only ? h : mr.cov(h);
         }
     const bool sym = a.mode != CM_RECT;
+    const double diag_add = m.diag_add;
     const bool diag_tile = sym && ti == tj;
+    // interior tiles (all but the edge and diagonal ones): no bounds or triangle tests, 16-byte stores
+    const bool interior = !diag_tile && a.vec_ok && r0 + CT <= a.n && c0 + CT <= a.mcols;
+    if (interior) {
+        double* kp = Kb + (long long)(r0 + ty * 4) * a.ldk + c0 + 2 * tx;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = r0 + ty * 4 + i;
-        if (row >= a.n) continue;
+        for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<double2*>(kp) = make_double2(v[i][0], v[i][1]);
+            *reinterpret_cast<double2*>(kp + 32) = make_double2(v[i][2], v[i][3]);
+            kp += a.ldk;
+        }
+    } else {
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int col = c0 + 32 * b + 2 * tx;
-            double v0 = v[i][2 * b], v1 = v[i][2 * b + 1];
-            if (diag_tile && !a.dist_only) {
-                if (col == row) v0 += m.diag_add;
-                if (col + 1 == row) v1 += m.diag_add;
-            }
-            double* kp = Kb + (long long)row * a.ldk + col;
-            const bool lower_only = a.mode == CM_SYM_LOWER && diag_tile;
-            const bool w0 = col < a.mcols && (!lower_only || col <= row);
-            const bool w1 = col + 1 < a.mcols && (!lower_only || col + 1 <= row);
-            if (w0 && w1 && a.vec_ok) {
-                *reinterpret_cast<double2*>(kp) = make_double2(v0, v1);
-            } else {
-                if (w0) kp[0] = v0;
-                if (w1) kp[1] = v1;
+        for (int i = 0; i < 4; ++i) {
+            const int row = r0 + ty * 4 + i;
+            if (row >= a.n) continue;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int col = c0 + 32 * b + 2 * tx;
+                double v0 = v[i][2 * b], v1 = v[i][2 * b + 1];
+                if (diag_tile && !a.dist_only) {
+                    if (col == row) v0 += diag_add;
+                    if (col + 1 == row) v1 += diag_add;
+                }
+                double* kp = Kb + (long long)row * a.ldk + col;
+                const bool lower_only = a.mode == CM_SYM_LOWER && diag_tile;
+                const bool w0 = col < a.mcols && (!lower_only || col <= row);
+                const bool w1 = col + 1 < a.mcols && (!lower_only || col + 1 <= row);
+                if (w0 && w1 && a.vec_ok) {
+                    *reinterpret_cast<double2*>(kp) = make_double2(v0, v1);
+                } else {
+                    if (w0) kp[0] = v0;
+                    if (w1) kp[1] = v1;
+                }
             }
         }
     }
@@ -248,7 +331,14 @@ int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batc
     bytes += 8.0 * (double)(n + (same ? 0 : a.mcols)) * spec->d;
     LaunchScope scope(KC_MATERN, bytes * batch, stream);
     dim3 grid((unsigned)ntiles, 1, (unsigned)batch);
-    matern_cov_kernel<<<grid, COV_THREADS, 0, stream>>>(a);
+    switch (dist_only ? 0 : spec->p) {
+        case 0: matern_cov_kernel<0><<<grid, COV_THREADS, 0, stream>>>(a); break;
+        case 1: matern_cov_kernel<1><<<grid, COV_THREADS, 0, stream>>>(a); break;
+        case 2: matern_cov_kernel<2><<<grid, COV_THREADS, 0, stream>>>(a); break;
+        case 3: matern_cov_kernel<3><<<grid, COV_THREADS, 0, stream>>>(a); break;
+        case 4: matern_cov_kernel<4><<<grid, COV_THREADS, 0, stream>>>(a); break;
+        default: matern_cov_kernel<-1><<<grid, COV_THREADS, 0, stream>>>(a); break;
+    }
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
 }
@@ -312,11 +402,16 @@ struct ContractArgs {
     double* partial;  // [nblocks][2 + d]
 };
 
+template <int P>
 __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArgs a) {
     __shared__ __align__(16) double xs[GPMP_MAX_DIM][CT];
     __shared__ __align__(16) double ys[GPMP_MAX_DIM][CT];
     __shared__ double wacc[COV_THREADS / 32][GPMP_MAX_DIM + 2];
-    const MaternDev& m = a.m;
+    __shared__ MaternDev msh;
+    stage_matern(&msh, nullptr, a.m);
+    const MaternDev& m = msh;
+    MaternRegs<P> mr;
+    mr.init(&msh);
     int ti, tj;
     if (a.sym) tri_decode(blockIdx.x, ti, tj);
     else { ti = blockIdx.x / a.tiles_n; tj = blockIdx.x - ti * a.tiles_n; }
@@ -366,19 +461,18 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
                 gv = a.G[(long long)row * a.ldg + col];
                 for (int q = 0; q < a.r; ++q) gv -= a.Ut[(long long)q * a.ldu + row] * a.Ut[(long long)q * a.ldu + col];
             }
-            const double h = sqrt(h2[i][k]);
+            const double h = fast_sqrt(h2[i][k]);
             double dkh, kc;
             if (a.dist_only) {
                 dkh = h > 0.0 ? 1.0 / h : 0.0;  // reference: custom_sqrt has zero gradient at 0
                 kc = 0.0;
             } else {
-                dkh = matern_dk_over_h(m, h);
+                mr.cov_and_dk(h, kc, dkh);  // both already carry sigma2
                 if (m.p == 0) dkh = h > 0.0 ? dkh / h : 0.0;  // reference: masked sqrt gradient at 0
-                kc = m.sigma2 * matern_k(m, h);
             }
             sK += mult * gv * kc;
             if (a.same_set && live && row == col) sTr += gv;
-            w[i][k] = live ? mult * gv * m.sigma2 * dkh : 0.0;
+            w[i][k] = live ? mult * gv * dkh : 0.0;
         }
     }
     // per-dimension sums: warp-reduce each, lane 0 keeps the warp's running value in smem
@@ -467,7 +561,14 @@ int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const dou
     {
         double bytes = sym ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
         LaunchScope scope(KC_CONTRACT, bytes, stream);
-        contract_kernel<<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a);
+        switch (dist_only ? 0 : spec->p) {
+            case 0: contract_kernel<0><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
+            case 1: contract_kernel<1><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
+            case 2: contract_kernel<2><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
+            case 3: contract_kernel<3><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
+            case 4: contract_kernel<4><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
+            default: contract_kernel<-1><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
+        }
         GPMP_CHECK_LAUNCH();
     }
     ContractFinalArgs f;

@@ -72,17 +72,6 @@ __device__ __forceinline__ void smem_mma(int M8, int N8, int wid, int nw, FA a, 
     }
 }
 
-// 1/sqrt(a) in double from the single-precision MUFU seed and two Newton steps (the library rsqrt()
-// is a long software sequence; this one sits on the per-column critical chain of the tile factor).
-__device__ __forceinline__ double fast_rsqrt(double a) {
-    if (!(a > 1e-30 && a < 1e30)) return rsqrt(a);
-    double y = (double)rsqrtf((float)a);
-    const double h = 0.5 * a;
-    y = y * fma(-h * y, y, 1.5);  // 22 -> 44 bits
-    y = y * fma(-h * y, y, 1.5);  // -> full double
-    return y;
-}
-
 // Factor one 128x128 diagonal tile (lower) and invert the factor.  One CTA per tile.
 //
 // The tile lives in shared memory for the whole kernel:  S lower = L,  S strict upper = T^T
