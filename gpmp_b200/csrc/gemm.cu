@@ -14,7 +14,6 @@
 // Shared tiles are dense 128-byte rows with the 16-byte chunk index XOR-swizzled by (row & 7) -- the
 // layout a TMA SWIZZLE_128B box produces.  Inside a K chunk the k index is permuted (lane kk owns
 // k = 4*kk + s at MMA step s) so each lane fetches its 4 steps with two conflict-free LDS.128.
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace gpmp {
@@ -207,12 +206,14 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKA
 template <int WM, int WN, int MI, int NI, int MINB, int STAGES = 3, int SUBK = 2>
 static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     using Cfg = GemmCfg<WM, WN, MI, NI, STAGES, SUBK>;
-    static bool configured = false;
+    static unsigned long long configured = 0;  // one bit per device: the attribute is per context
     auto kern = gemm_nt_kernel<WM, WN, MI, NI, MINB, STAGES, SUBK>;
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
             return GPMP_ERR_CUDA;
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     GemmKArgs a;
     a.g = g;
@@ -251,14 +252,7 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
     // big CTA cannot (the DMMA pipe sat at 85 % with 1 CTA/SM).  An in-place product (the single-column-tile
     // panel solves, A == C) must keep one column tile per row block, so N > 64 takes the 128-wide shape.
     const bool in_place = (g.A == g.C || g.B == g.C);
-    static int big_cfg = -1;
-    if (big_cfg < 0) {
-        const char* e = getenv("GPMP_GEMM_CFG");
-        big_cfg = e ? atoi(e) : 6;
-    }
     if (in_place && g.N > 64) return launch_cfg<4, 4, 4, 4, 1>(g, stream);
-    if (big_cfg == 1) return launch_cfg<4, 4, 4, 4, 1>(g, stream);  // development switch
-    if (big_cfg == 4) return launch_cfg<2, 2, 4, 4, 3, 4, 1>(g, stream);  // 3 CTAs/SM, 4 stages (development)
     return launch_cfg<2, 2, 4, 4, 4, 3, 1>(g, stream);
 }
 

@@ -9,11 +9,15 @@
 // K-range trimming in the GEMM is at 128-tile granularity, which is why diagonal tiles carry real
 // zeros and why every block boundary used below is a multiple of 128.
 //
-// gpmp_potrf: two-level right-looking factorisation.  Outer block NB (128/256/512): the NB diagonal
-// block is factored by 128-wide sub-steps (potf2 tile kernel -> in-place TRSM by the tile inverse ->
-// SYRK), its inverse is assembled by block doubling (inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1,C^-1]]),
-// the panel below is solved with ONE GEMM against that inverse and the trailing matrix gets ONE
-// K=NB SYRK.  Extra rows n..nrows-1 ride along in every panel solve (they leave as B L^-T).
+// gpmp_potrf: right-looking factorisation in column groups of NB (128/256/512) columns.  Inside a group,
+// 128-wide steps: tile kernel (factor + inverse of the 128x128 diagonal tile), solve of ALL rows below by
+// one GEMM against the tile inverse (into the group's panel buffer), copy-back + mirror, K=128 update of
+// the group's remaining columns.  After the group's last step the buffer holds its complete solved panel
+// and the trailing matrix gets ONE K=NB SYRK (lower tiles).  Extra rows n..nrows-1 ride along in every
+// solve (they leave as B L^-T).  The NB-wide inverses of the diagonal blocks, which the triangular inverse
+// and the row solves start from, are assembled afterwards by block doubling
+// (inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1,C^-1]]).  Single large matrices run a three-stream
+// look-ahead (potrf_core); the same pieces serve the panel-partitioned multi-GPU loop (dist_*).
 #include <vector>
 #include "internal.cuh"
 
@@ -393,12 +397,14 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
 }
 
 static int launch_potf2(const Potf2Args& a, int batch, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;  // one bit per device: the attribute is per context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
         if (cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM) !=
             cudaSuccess)
             return GPMP_ERR_CUDA;
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     LaunchScope scope(KC_POTF2, (double)batch * (PT * (double)PT * PT), stream);  // n^3/3 + 2n^3/3
     potf2_kernel<<<batch, POTF2_THREADS, POTF2_SMEM, stream>>>(a);

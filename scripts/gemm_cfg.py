@@ -1,4 +1,4 @@
-"""DMMA GEMM throughput for the current GPMP_GEMM_CFG (development aid)."""
+"""DMMA GEMM throughput at several K (development aid; the tile shapes it once compared are listed in gemm.cu)."""
 import json
 import os
 import sys
@@ -25,7 +25,7 @@ n = 8192
 A = torch.randn(n, n, dtype=torch.float64, device="cuda")
 B = torch.randn(n, n, dtype=torch.float64, device="cuda")
 C = torch.zeros(n, n, dtype=torch.float64, device="cuda")
-out = {"cfg": os.environ.get("GPMP_GEMM_CFG", "0")}
+out = {}
 out["gemm_8192"] = 2 * n**3 / ev(lambda: ops.gemm_nt(A, B, C_out=C)) / 1e9
 for k in (128, 256, 512, 1024):
     Ak = A[:, :k].contiguous()
