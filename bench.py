@@ -133,7 +133,7 @@ def run_reference(args):
         return
     # full size when the run stays within a few minutes (one evaluation is ~7-25 s of host time),
     # otherwise n = 4096 scaled by n^3 (the O(n^2 d) terms make the scaled figure slightly pessimistic)
-    n_s = N_OBS if (args.steps + args.warmup) <= 8 else 4096
+    n_s = args.ref_n if args.ref_n else (N_OBS if (args.steps + args.warmup) <= 8 else 4096)
     scale = (N_OBS / n_s) ** 3
     for _ in range(args.warmup):
         cpu_eval_seconds(n_s, DIM)
@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpmp_b200", choices=["gpmp_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-n", type=int, default=0, help="reference arm: sample size override (tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":

@@ -77,6 +77,7 @@ SIGNATURES = {
     "gpmp_predict_scratch_bytes": (_sz, [_i, _i, _i]),
     "gpmp_predict_chunk": (_i, [_specp, _vp, _i, _i, _vp, _sz, _vp, _i, _vp, _vp, _vp, _ll, _vp, _sz, _vp, _vp,
                                 _i, _vp]),
+    "gpmp_lik_trsm_rows": (_i, [_i, _i, _vp, _sz, _vp, _i, _ll, _i, _vp, _vp]),
     "gpmp_criterion_batched_bytes": (_sz, [_i, _i, _i]),
     "gpmp_criterion_batched": (_i, [_specp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp]),
 }

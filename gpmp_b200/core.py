@@ -138,6 +138,19 @@ class Model:
         state, out = self._fit(xi, zi, self._basis(xi), _as_param(covparam))
         return torch.tensor(ops.read_small(out)[2], dtype=torch.float64)
 
+    def k_inverses(self, xi, zi, covparam):
+        """(z^T K^-1 z, K^-1 1, K^-1 z)  (core/linalg.py:121-129), by one factorisation with z and the ones
+        vector carried as right-hand-side rows (no explicit inverse)."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
+        with torch.no_grad():
+            K = kernel.materialize(self.covariance(xi, xi, _as_param(covparam)))
+            rhs = torch.stack((zi, torch.ones_like(zi)))
+            fac = ops.potrf(K, extra_rows=rhs)
+            rows = fac.A[fac.n:, :]
+            ops.trsm_rows(fac, rows, trans=1)
+            kinv_z, kinv_1 = rows[0, : fac.n].clone(), rows[1, : fac.n].clone()
+            return torch.dot(zi, kinv_z), kinv_1, kinv_z
+
     # ------------------------------------------------------------------ prediction
     def _fit(self, xi, zi, P, covparam, with_inverse=False):
         """Factor K(xi, xi) with zi (and P) whitened along -> (FitState, out_dev)."""
@@ -179,6 +192,32 @@ class Model:
             return num.to_np(zloo), num.to_np(s2), num.to_np(e)
         return zloo, s2, e
 
+    def fit(self, xi, zi, state=None):
+        """Factor K(xi, xi) once (zi and the mean basis whitened along) and return a `Fitted` handle whose
+        predict / conditional_sample_paths_chunked reuse the factor.  `state` lets a caller supply a fitted
+        state computed elsewhere (gpmp_b200.dist.fit_distributed: factorisation partitioned over GPUs)."""
+        xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
+        covparam = _as_param(self.covparam)
+        P = None
+        zc, zi_prior = zi, None
+        if self.meantype == "linear_predictor":
+            P = self._basis(xi)
+        elif self.meantype == "parameterized":
+            if self.meanparam is None:
+                raise ValueError("For meantype 'parameterized', meanparam should not be None.")
+            zi_prior = ops.to_device(self.mean(xi, _as_param(self.meanparam))).reshape(-1)
+            zc = zi - zi_prior
+        elif self.meantype != "zero":
+            raise ValueError(f"Invalid meantype {self.meantype}.")
+        if state is None:
+            with torch.no_grad():
+                state, out = self._fit(xi, zc, P, covparam)
+                if ops.read_small(out)[6] != 0.0:
+                    raise torch.linalg.LinAlgError("fit: K(xi, xi) is not positive-definite")
+        elif state.spec is not None:
+            state.kernel = (state.spec.p, covparam)  # lets the chunks recognise the plain Matern cross-covariance
+        return Fitted(self, state, xi, zc, covparam)
+
     def predict(self, xi, zi, xt, return_lambdas=False, zero_neg_variances=True, convert_in=True,
                 convert_out=True):
         """Posterior mean / variance at xt given (xi, zi)  (core/model.py:227-307).
@@ -188,75 +227,8 @@ class Model:
         Returns (mean[nt], var[nt]) as NumPy arrays (convert_out) or device tensors, plus the kriging
         weights lambda_t (ni x nt, device) when return_lambdas.
         """
-        xi, zi, xt = _ensure_shapes_and_type(xi=xi, zi=zi, xt=xt, convert=convert_in)
-        covparam = _as_param(self.covparam)
-        n, m = xi.shape[0], xt.shape[0]
-        P = Pt = None
-        zt_prior_mean = None
-        zc = zi
-        if self.meantype == "linear_predictor":
-            P = self._basis(xi)
-            Pt = self._basis(xt).contiguous()
-        elif self.meantype == "parameterized":
-            if self.meanparam is None:
-                raise ValueError("For meantype 'parameterized', meanparam should not be None.")
-            mp = _as_param(self.meanparam)
-            zc = zi - ops.to_device(self.mean(xi, mp)).reshape(-1)
-            zt_prior_mean = ops.to_device(self.mean(xt, mp)).reshape(-1)
-        elif self.meantype != "zero":
-            raise ValueError(f"Invalid meantype {self.meantype}.")
-
-        with torch.no_grad():
-            state, out = self._fit(xi, zc, P, covparam)
-            if ops.read_small(out)[6] != 0.0:
-                raise torch.linalg.LinAlgError("predict: K(xi, xi) is not positive-definite")
-            ktt = ops.to_device(self.covariance(xt, None, covparam, pairwise=True)).reshape(-1).contiguous()
-            ld = ops._round_ld(n)
-            chunk = int(max(128, min(32768, (1 << 31) // (8 * ld))))
-            lam_rows = ops._empty((m, ld)) if return_lambdas else None
-            mean = ops._empty((m,))
-            var = ops._empty((m,))
-            for c0 in range(0, m, chunk):
-                c1 = min(m, c0 + chunk)
-                xtc = xt[c0:c1]
-                Vt = lam_rows[c0:c1] if return_lambdas else ops._empty((c1 - c0, ld))
-                fused = state.spec is not None
-                if fused:
-                    with kernel.capture():
-                        Kx = self.covariance(xi, xtc, covparam)
-                    same_kernel = (isinstance(Kx, kernel.LazyMatern) and Kx.y is xtc and Kx.x is xi
-                                   and Kx.p == state.kernel[0] and Kx.param is state.kernel[1])
-                    if not same_kernel:
-                        # the cross-covariance is not the plain Matern of the same-set call: take what the
-                        # callable returns (the solve below only needs K(xt, xi) as rows)
-                        Vt[:, :n].copy_(kernel.materialize(Kx).t())
-                        saved, state.spec = state.spec, None
-                        try:
-                            mu, s2 = ops.predict_chunk(state, xtc, None if Pt is None else Pt[c0:c1],
-                                                       ktt[c0:c1], Vt, return_lambdas)
-                        finally:
-                            state.spec = saved
-                    else:
-                        mu, s2 = ops.predict_chunk(state, xtc, None if Pt is None else Pt[c0:c1], ktt[c0:c1], Vt,
-                                                   return_lambdas)
-                else:
-                    Kx = kernel.materialize(self.covariance(xi, xtc, covparam))
-                    Vt[:, :n].copy_(Kx.t())
-                    mu, s2 = ops.predict_chunk(state, xtc, None if Pt is None else Pt[c0:c1], ktt[c0:c1], Vt,
-                                               return_lambdas)
-                mean[c0:c1] = mu
-                var[c0:c1] = s2
-            if zt_prior_mean is not None:
-                mean = mean + zt_prior_mean
-            if bool((var < 0.0).any()):
-                warnings.warn("Negative variances detected. Consider using jitter.", RuntimeWarning)
-            if zero_neg_variances:
-                var = torch.clamp_min(var, 0.0)
-        if convert_out:
-            mean, var = num.to_np(mean), num.to_np(var)
-        if return_lambdas:
-            return mean, var, lam_rows[:, :n].t()
-        return mean, var
+        return self.fit(xi, zi).predict(xt, return_lambdas=return_lambdas, zero_neg_variances=zero_neg_variances,
+                                        convert_out=convert_out)
 
     # ------------------------------------------------------------------ sample paths
     def sample_paths(self, xt, nb_paths, method="chol", check_result=True):
@@ -313,6 +285,105 @@ class Model:
             ops.gemm_nt(lamT, ops.transpose(delta), C_out=out, alpha=1.0, beta=1.0)
             if zt_prior is not None:
                 out = out + zt_prior
+            out = out.contiguous()
+        return num.to_np(out) if convert_out else out
+
+
+class Fitted:
+    """A model fitted to (xi, zi): the device factor L (both ways), the whitened data, Q~ / R~ of the whitened
+    mean basis.  Everything that follows the factorisation -- prediction, kriging weights, conditioning of
+    sample paths -- streams test points through it chunk by chunk; lambda_t is formed only on request."""
+
+    def __init__(self, model, state, xi, zc, covparam):
+        self.model, self.state, self.xi, self.zc, self.covparam = model, state, xi, zc, covparam
+        self.n = xi.shape[0]
+        self.ld = ops._round_ld(self.n)
+        self.chunk = int(max(128, min(32768, (1 << 31) // (8 * self.ld))))
+
+    def _chunk(self, xtc, Pt, ktt, Vt, mode):
+        """One chunk through gpmp_predict_chunk; takes the callable's own cross-covariance when it is not the
+        plain Matern of the same-set call."""
+        model, state, n = self.model, self.state, self.n
+        if state.spec is not None:
+            with kernel.capture():
+                Kx = model.covariance(self.xi, xtc, self.covparam)
+            same = (isinstance(Kx, kernel.LazyMatern) and Kx.y is xtc and Kx.x is self.xi
+                    and getattr(state, "kernel", None) is not None and Kx.p == state.kernel[0]
+                    and Kx.param is state.kernel[1])
+            if same:
+                return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode)
+            Vt[:, :n].copy_(kernel.materialize(Kx).t())
+            saved, state.spec = state.spec, None
+            try:
+                return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode)
+            finally:
+                state.spec = saved
+        Kx = kernel.materialize(model.covariance(self.xi, xtc, self.covparam))
+        Vt[:, :n].copy_(Kx.t())
+        return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode)
+
+    def _basis_and_prior(self, xt):
+        model = self.model
+        Pt = model._basis(xt).contiguous() if model.meantype == "linear_predictor" else None
+        prior = None
+        if model.meantype == "parameterized":
+            prior = ops.to_device(model.mean(xt, _as_param(model.meanparam))).reshape(-1)
+        return Pt, prior
+
+    def predict(self, xt, return_lambdas=False, zero_neg_variances=True, convert_out=True):
+        xt = ops.to_device(xt)
+        assert xt.dim() == 2 and xt.shape[1] == self.xi.shape[1], "xi and xt must have the same number of columns"
+        n, m = self.n, xt.shape[0]
+        with torch.no_grad():
+            Pt, prior = self._basis_and_prior(xt)
+            ktt = ops.to_device(self.model.covariance(xt, None, self.covparam, pairwise=True)).reshape(-1).contiguous()
+            lam_rows = ops._empty((m, self.ld)) if return_lambdas else None
+            mean, var = ops._empty((m,)), ops._empty((m,))
+            for c0 in range(0, m, self.chunk):
+                c1 = min(m, c0 + self.chunk)
+                Vt = lam_rows[c0:c1] if return_lambdas else ops._empty((c1 - c0, self.ld))
+                mu, s2 = self._chunk(xt[c0:c1], None if Pt is None else Pt[c0:c1], ktt[c0:c1], Vt,
+                                     1 if return_lambdas else 0)
+                mean[c0:c1] = mu
+                var[c0:c1] = s2
+            if prior is not None:
+                mean = mean + prior
+            if bool((var < 0.0).any()):
+                warnings.warn("Negative variances detected. Consider using jitter.", RuntimeWarning)
+            if zero_neg_variances:
+                var = torch.clamp_min(var, 0.0)
+        if convert_out:
+            mean, var = num.to_np(mean), num.to_np(var)
+        if return_lambdas:
+            return mean, var, lam_rows[:, :n].t()
+        return mean, var
+
+    def conditional_sample_paths_chunked(self, ztsim, xi_ind, xt, xt_ind, convert_out=True):
+        """Conditioning by kriging without ever forming lambda_t (the reference's
+        core/sample_paths.py:66-182 needs the ni x nt weights, 262 GB at n=32768, nt=1e6):
+            ztsimc = ztsim[xt_ind] + W delta~^T (+ prior mean),   W rows = v_t - Q~ e_t,  delta~ = L^-1 delta
+        where delta = zi (centred) - ztsim[xi_ind].  One predict chunk + one DMMA GEMM per chunk of xt."""
+        xt = ops.to_device(xt)
+        with torch.no_grad():
+            zs = ops.to_device(ztsim)
+            dev = zs.device
+            xi_ind = torch.as_tensor(np.asarray(xi_ind).reshape(-1), dtype=torch.long, device=dev)
+            xt_ind = torch.as_tensor(np.asarray(xt_ind).reshape(-1), dtype=torch.long, device=dev)
+            n, m, npaths = self.n, xt.shape[0], zs.shape[1]
+            delta_rows = ops.transpose(self.zc.reshape(-1, 1) - zs[xi_ind, :])  # paths x n
+            ops.lik_trsm_rows(self.state, delta_rows, trans=0)
+            Pt, prior = self._basis_and_prior(xt)
+            ktt = ops.to_device(self.model.covariance(xt, None, self.covparam, pairwise=True)).reshape(-1).contiguous()
+            out = ops._empty((m, ops._round_ld(npaths)))[:, :npaths]
+            for c0 in range(0, m, self.chunk):
+                c1 = min(m, c0 + self.chunk)
+                Vt = ops._empty((c1 - c0, self.ld))
+                self._chunk(xt[c0:c1], None if Pt is None else Pt[c0:c1], ktt[c0:c1], Vt, 2)
+                oc = out[c0:c1]
+                oc.copy_(zs[xt_ind[c0:c1], :])
+                ops.gemm_nt(Vt[:, :n], delta_rows, C_out=oc, alpha=1.0, beta=1.0)
+            if prior is not None:
+                out = out + prior.reshape(-1, 1)
             out = out.contiguous()
         return num.to_np(out) if convert_out else out
 

@@ -496,10 +496,25 @@ int gpmp_predict_chunk(const gpmp_cov_spec* spec, const double* x_dev, int n, in
     if (want_lambda) {
         rc = launch_wrows(rd, s);
         if (rc) return rc;
-        rc = trsm_rows_core(A, n, w.lda, w.pw.NB, Tlo_c, Tup_c, Vt_dev, m, ldv, 1, Wsc, s);
-        if (rc) return rc;
+        if (want_lambda == 1) {
+            rc = trsm_rows_core(A, n, w.lda, w.pw.NB, Tlo_c, Tup_c, Vt_dev, m, ldv, 1, Wsc, s);
+            if (rc) return rc;
+        }
     }
     return GPMP_OK;
+}
+
+int gpmp_lik_trsm_rows(int n, int q, void* work_dev, size_t work_bytes, double* Bt_dev, int m, long long ldb,
+                       int trans, void* scratch_dev, void* stream) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !Bt_dev || !scratch_dev || m < 0) return GPMP_ERR_ARG;
+    if (ldb & 1) return GPMP_ERR_ALIGN;
+    LikWs w = lik_ws(n, q, 1);
+    if (work_bytes < w.total_value) return GPMP_ERR_WORKSPACE;
+    char* base = static_cast<char*>(work_dev);
+    char* pb = base + w.off_potrf;
+    return trsm_rows_core((double*)(base + w.off_A), n, w.lda, w.pw.NB, (const double*)(pb + w.pw.off_tlo),
+                          (const double*)(pb + w.pw.off_tup), Bt_dev, m, ldb, trans, (double*)scratch_dev,
+                          (cudaStream_t)stream);
 }
 
 // ---- batched criterion -----------------------------------------------------------------------------

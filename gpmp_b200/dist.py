@@ -67,16 +67,26 @@ def reml_value_distributed(model, covparam, xi, zi, group=None):
     return ops.read_small(out)[0], state
 
 
-def predict_distributed(model, xi, zi, xt, group=None, convert_out=True):
+def fit_distributed(model, xi, zi, group=None):
+    """Model.fit with the factorisation partitioned over the ranks of `group`: every rank returns a `Fitted`
+    handle holding the complete factor (model.covparam / meanparam are used, as in Model.predict)."""
+    _, state = reml_value_distributed(model, model.covparam, xi, zi, group)
+    return model.fit(xi, zi, state=state)
+
+
+def predict_distributed(model, xi, zi, xt, group=None, convert_out=True, fitted=None):
     """Model.predict with the test points block-partitioned over the ranks of `group` (independent columns,
-    SURVEY.md 8e): every rank fits (xi, zi) -- replicated, or use reml_value_distributed first for one large
-    factorisation -- predicts its block of xt and the (mean, variance) vectors are all-gathered."""
-    from . import num
+    SURVEY.md 8e).  `fitted`: a handle from fit_distributed / Model.fit (otherwise every rank fits locally);
+    each rank predicts its block of xt and the (mean, variance) vectors are all-gathered."""
+    from . import num, ops
 
     rank, size = world(group)
+    xt = ops.to_device(xt)
     m = xt.shape[0]
     lo, hi = block_bounds(m, rank, size)
-    mean, var = model.predict(xi, zi, xt[lo:hi], convert_out=False)
+    if fitted is None:
+        fitted = model.fit(xi, zi)
+    mean, var = fitted.predict(xt[lo:hi], convert_out=False)
     mean = all_gather_rows(mean, m, group)
     var = all_gather_rows(var, m, group)
     if convert_out:

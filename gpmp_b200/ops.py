@@ -474,6 +474,15 @@ def lik_loo(state, z):
     return zloo, s2, e
 
 
+def lik_trsm_rows(state, Bt, trans):
+    """Row solves (trans=0: b -> L^-1 b, trans=1: b -> L^-T b) against the factor held in a fitted state."""
+    m = Bt.shape[0]
+    scratch = _workspace(max(m, 1) * 512 * 8)
+    check(lib().gpmp_lik_trsm_rows(state.n, state.q, ptr(state.work), state.work.numel(), ptr(Bt), m, _ld(Bt),
+                                   int(trans), ptr(scratch), stream_ptr()), "gpmp_lik_trsm_rows")
+    return Bt
+
+
 def _scalar_like(param, value):
     t = torch.tensor(value, dtype=F64)
     if torch.is_tensor(param) and param.device.type != "cpu":
@@ -563,7 +572,8 @@ def likelihood_from_K(K, z, P):
 # --------------------------------------------------------------------------------------------------
 def predict_chunk(state, xt, Pt, ktt, Vt, want_lambda):
     """One chunk of test points against a fitted state; returns (mean, var) device vectors; Vt is
-    overwritten (rows lambda_t^T when want_lambda)."""
+    overwritten: want_lambda = 0 scratch, 1 rows lambda_t^T, 2 rows w_t = v_t - Q~ e_t (the kriging weights
+    in whitened coordinates: lambda_t = L^-T w_t)."""
     m = Vt.shape[0]
     n, q = state.n, state.q
     sbytes = lib().gpmp_predict_scratch_bytes(n, q, m)
@@ -572,7 +582,7 @@ def predict_chunk(state, xt, Pt, ktt, Vt, want_lambda):
     spec = state.spec
     check(lib().gpmp_predict_chunk(C.byref(spec) if spec is not None else None, ptr(state.x), n, q, ptr(state.work),
                                    state.work.numel(), ptr(xt), m, ptr(Pt), ptr(ktt), ptr(Vt), _ld(Vt),
-                                   ptr(scratch), scratch.numel(), ptr(mean), ptr(var), 1 if want_lambda else 0,
+                                   ptr(scratch), scratch.numel(), ptr(mean), ptr(var), int(want_lambda),
                                    stream_ptr()), "gpmp_predict_chunk")
     return mean, var
 

@@ -202,13 +202,21 @@ int gpmp_lik_loo(int n, int q, void* work_dev, size_t work_bytes, const double* 
  *   Vt_dev (m x ldv, ldv >= n): spec != NULL -> filled here with K(xt, xi); spec == NULL -> the caller
  *     has put a user-composed K(xt, xi) there.  On exit: rows lambda_t^T if want_lambda, else scratch.
  *   Pt_dev (m x q) mean basis at xt (NULL when q == 0);  ktt_dev[m] prior variances (NULL: sigma2).
- *   mean_dev[m], var_dev[m] outputs (variance not clamped: Model.predict clamps and warns). */
+ *   mean_dev[m], var_dev[m] outputs (variance not clamped: Model.predict clamps and warns).
+ *   want_lambda: 0 Vt is scratch on exit; 1 rows lambda_t^T; 2 rows w_t = v_t - Q~ e_t, the kriging weights in
+ *   whitened coordinates (lambda_t = L^-T w_t): conditioning of sample paths needs only W (L^-1 delta)^T, so
+ *   the n x m weight matrix of gpmp/core/sample_paths.py:66-182 is never formed. */
 size_t gpmp_predict_scratch_bytes(int n, int q, int m);
 int gpmp_predict_chunk(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, void* work_dev,
                        size_t work_bytes, const double* xt_dev, int m, const double* Pt_dev,
                        const double* ktt_dev, double* Vt_dev, long long ldv, void* scratch_dev,
                        size_t scratch_bytes, double* mean_dev, double* var_dev, int want_lambda,
                        void* stream);
+
+/* Row solves against the factor held in a likelihood workspace (after gpmp_lik_value / gpmp_lik_dist_finish):
+ * rows of Bt (m x n): trans == 0  b -> L^-1 b,  trans == 1  b -> L^-T b.  scratch_dev: m x 512 doubles. */
+int gpmp_lik_trsm_rows(int n, int q, void* work_dev, size_t work_bytes, double* Bt_dev, int m, long long ldb,
+                       int trans, void* scratch_dev, void* stream);
 
 /* ---- batched criterion (replaces the serial loop of gpmp/mcmc/param_posterior.py:739-759): N
  * independent REML / ML values at theta_1..theta_N on fixed (x, z, P).  theta_dev: N x (1+noise+d)

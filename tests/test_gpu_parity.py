@@ -200,6 +200,9 @@ def test_likelihoods_and_gradients(gp, golden_np, golden_t, case):
     v = m.negative_log_likelihood_zero_mean(th, x, z)
     assert relerr(v.item(), gn["nll_zero"]) <= TOL_LIK
     assert relerr(m.norm_k_sqrd_with_zero_mean(x, z, th).item(), gn["norm_zero"]) <= TOL_LIK
+    zkz, ki1, kiz = m.k_inverses(x, z, th)
+    assert relerr(zkz.item(), gn["kinv_zkz"]) <= TOL_LIK
+    assert relerr_norm(ki1.cpu().numpy(), gn["kinv_1"]) <= 1e-7 and relerr_norm(kiz.cpu().numpy(), gn["kinv_z"]) <= 1e-7
     # gradients against the torch-backend reference (autograd through every op)
     tp = torch.tensor(th, requires_grad=True)
     v = m.negative_log_likelihood_zero_mean(tp, x, z)
@@ -317,6 +320,12 @@ def test_predict_and_conditioning(gp, golden_np, case):
         cond = m.conditional_sample_paths(g["ztsim"], xi_ind, z, xt_ind, lam)
     assert cond.shape == g["cond"].shape
     assert np.max(np.abs(cond - g["cond"])) / max(1.0, float(np.max(np.abs(g["cond"])))) <= 1e-8
+    # the chunked form never builds lambda_t: W (L^-1 delta)^T per chunk of xt
+    fit = m.fit(x, z)
+    cond2 = fit.conditional_sample_paths_chunked(g["ztsim"], xi_ind, xt, xt_ind)
+    assert np.max(np.abs(cond2 - g["cond"])) / max(1.0, float(np.max(np.abs(g["cond"])))) <= 1e-8
+    mean3, var3 = fit.predict(xt)
+    assert np.array_equal(mean3, mean2) and np.array_equal(var3, var2)
     # the deterministic half of sample_paths: C @ normals with K(xt, xt) = C C^T
     normals = np.random.default_rng(1).standard_normal((mt, 3))
     zs = m.sample_paths_from_normals(xt, normals).cpu().numpy()
@@ -424,6 +433,12 @@ def test_partitioned_factorisation_matches_local(gp):
     mean, var = gp.dist.predict_distributed(m, x, z, xt)
     mean1, var1 = m.predict(x, z, xt)
     assert np.array_equal(mean, mean1) and np.array_equal(var, var1)
+    m.covparam = th
+    fitted = gp.dist.fit_distributed(m, x, z)
+    mean2, var2 = gp.dist.predict_distributed(m, x, z, xt, fitted=fitted)
+    # the partitioned path re-derives the tile inverses from the received factor (1 / L_ii instead of the
+    # factorisation's own rsqrt), so predictions agree to rounding, not bit for bit
+    assert relerr_norm(mean2, mean1) <= 1e-12 and relerr_norm(var2, var1) <= 1e-12
 
 
 # ----------------------------------------------------------------------------------------------------

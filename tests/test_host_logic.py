@@ -69,7 +69,7 @@ def test_bench_inputs_are_the_seeded_headline_case():
 def test_bench_reference_arm_prints_contract_line():
     env = dict(os.environ, OMP_NUM_THREADS="4")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+                          "--warmup", "0", "--ref-n", "1024"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["value"] > 0
