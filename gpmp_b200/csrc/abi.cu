@@ -45,7 +45,7 @@ static inline long long round_ld(int n) { return ((long long)n + 15) / 16 * 16; 
 // ---- workspace layouts ---------------------------------------------------------------------------
 struct PotrfWs {
     int NB, nblk;
-    size_t off_tlo, off_tup, off_w, total;
+    size_t off_tlo, off_tup, off_w, off_tsub, total;
 };
 static PotrfWs potrf_ws(int n, int nrows) {
     PotrfWs w;
@@ -56,7 +56,9 @@ static PotrfWs potrf_ws(int n, int nrows) {
     w.off_tup = align_up(tb, 256);
     w.off_w = w.off_tup + align_up(tb, 256);
     size_t wrows = (size_t)(nrows > w.NB ? nrows : w.NB);
-    w.total = w.off_w + align_up(2 * wrows * w.NB * 8, 256);  // two panel buffers (look-ahead)
+    w.off_tsub = w.off_w + align_up(2 * wrows * w.NB * 8, 256);  // two panel buffers (look-ahead)
+    // block-diagonal tile inverses for the chain's substitution solve: one 128x128 tile per 128 columns
+    w.total = w.off_tsub + align_up((size_t)ceil_div(n > 0 ? n : 1, 128) * 128 * 128 * 8, 256);
     return w;
 }
 
@@ -210,7 +212,8 @@ int gpmp_potrf(double* A_dev, int n, int nrows, long long lda, void* work_dev, s
     if (work_bytes < w.total) return GPMP_ERR_WORKSPACE;
     char* base = static_cast<char*>(work_dev);
     return potrf_core(A_dev, lda, 0, n, nrows, w.NB, (double*)(base + w.off_tlo), (double*)(base + w.off_tup), 0,
-                      (double*)(base + w.off_w), 0, info_dev, 0, 1, (cudaStream_t)stream);
+                      (double*)(base + w.off_w), 0, info_dev, 0, 1, (cudaStream_t)stream,
+                      (double*)(base + w.off_tsub));
 }
 
 int gpmp_potri(const double* L_dev, int n, long long ldl, const void* potrf_work_dev, double* Tlo_dev,
@@ -317,7 +320,8 @@ int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk
     if (rc) return rc;
     char* pb = base + w.off_potrf;
     rc = potrf_core((double*)(base + w.off_A), w.lda, 0, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo),
-                    (double*)(pb + w.pw.off_tup), 0, (double*)(pb + w.pw.off_w), 0, info_dev, 0, 1, s);
+                    (double*)(pb + w.pw.off_tup), 0, (double*)(pb + w.pw.off_w), 0, info_dev, 0, 1, s,
+                    (double*)(pb + w.pw.off_tsub));
     if (rc) return rc;
     return lik_finalize(n, q, w, base, out_dev, info_dev, s);
 }

@@ -36,8 +36,11 @@ struct Potf2Args {
     int* info; long long strideInfo;
     int row0;          // global index of the tile's first row (for info)
     long long* dbg;    // optional: clock64() at the phase boundaries (development only)
-    int invert_only;   // the tile already holds L (received from another rank): skip the factorisation
+    int mode;          // POTF2_FULL: factor + inverse; POTF2_INVERT: the tile already holds L, invert only;
+                       // POTF2_FACTOR: factor + the four 32x32 diagonal-block inverses only (block-diagonal T
+                       // into Tlo, Tup not written) -- what the substitution solve of the chain needs
 };
+enum { POTF2_FULL = 0, POTF2_INVERT = 1, POTF2_FACTOR = 2 };
 #define POTF2_STAMP(i)                                              \
     do {                                                            \
         if (a.dbg && threadIdx.x == 0) a.dbg[i] = clock64();        \
@@ -126,11 +129,11 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
 
     POTF2_STAMP(1);
     int bad = 0;  // 1-based local index of the first non-positive pivot (warp 0, lane 0 only)
-    if (a.invert_only) {
+    if (a.mode == POTF2_INVERT) {
         if (tid < PT) rinv[tid] = 1.0 / S[tid * PLD + tid];
         __syncthreads();
     }
-    for (int jb = 0; jb < (a.invert_only ? 0 : 4); ++jb) {
+    for (int jb = 0; jb < (a.mode == POTF2_INVERT ? 0 : 4); ++jb) {
         const int c0 = jb * 32;
         POTF2_STAMP(2 + 3 * jb);
         if (warp == 0) {
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
     POTF2_STAMP(15);
 
     // ---- inverse by doubling: 32 -> 64 (two pairs) -> 128, all warps -----------------------------------
+    if (a.mode != POTF2_FACTOR) {
     for (int pr = 0; pr < 2; ++pr) {
         const int a0 = 64 * pr, b0 = a0 + 32;
         double* Xp = X + pr * 32 * XLD;
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
             S[(j + 1) * PLD + 64 + i] = -c1v;
         });
     __syncthreads();
+    }
     POTF2_STAMP(17);
 
     // ---- write back: L (lower, zero upper) into A; T into Tlo (lower) / Tup (upper) -------------
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
         }
         if (a.Tlo) {
             double* __restrict__ Tlo = a.Tlo + zb * a.strideT + (long long)r * a.ldt + c;
-            double* __restrict__ Tup = a.Tup + zb * a.strideT + (long long)r * a.ldt + c;
+            double* __restrict__ Tup = a.Tup ? a.Tup + zb * a.strideT + (long long)r * a.ldt + c : nullptr;
             // T[r][c] lives at S[c][r] (r > c); T^T[r][c] = T[c][r] lives at S[r][c] (c > r)
             const double t0 = r > c ? S[c * PLD + r] : (r == c ? rinv[r] : 0.0);
             const double t1 = r > c + 1 ? S[(c + 1) * PLD + r] : (r == c + 1 ? rinv[r] : 0.0);
@@ -385,10 +390,14 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
             const double u1 = c + 1 > r ? S[r * PLD + c + 1] : (r == c + 1 ? rinv[r] : 0.0);
             if (vec && c + 1 < nb) {
                 *reinterpret_cast<double2*>(Tlo) = make_double2(t0, t1);
-                *reinterpret_cast<double2*>(Tup) = make_double2(u0, u1);
+                if (Tup) *reinterpret_cast<double2*>(Tup) = make_double2(u0, u1);
             } else {
-                Tlo[0] = t0; Tup[0] = u0;
-                if (c + 1 < nb) { Tlo[1] = t1; Tup[1] = u1; }
+                Tlo[0] = t0;
+                if (Tup) Tup[0] = u0;
+                if (c + 1 < nb) {
+                    Tlo[1] = t1;
+                    if (Tup) Tup[1] = u1;
+                }
             }
         }
     }
@@ -417,8 +426,144 @@ int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int*
                 cudaStream_t stream) {
     Potf2Args pa;
     pa.A = A; pa.lda = lda; pa.strideA = 0; pa.Tlo = Tlo; pa.Tup = Tup; pa.ldt = PT; pa.strideT = 0; pa.nb = nb;
-    pa.info = info; pa.strideInfo = 0; pa.row0 = 0; pa.dbg = dbg; pa.invert_only = 0;
+    pa.info = info; pa.strideInfo = 0; pa.row0 = 0; pa.dbg = dbg; pa.mode = POTF2_FULL;
     return launch_potf2(pa, 1, stream);
+}
+
+// ---- panel solve by blocked substitution (the chain's solve: needs only the 32x32 block inverses) ---------
+// X = P L^-T for the rows below a 128-wide tile: 64 rows per CTA, one 8-row strip per warp.  Rows are
+// independent, so after the operands are staged every warp walks its strip through the four 32-column block
+// steps on its own:  R_b = P_b - sum_{c<b} X_c L_bc^T  (DMMA, K = 32 b),  X_b = R_b T_bb^T  (DMMA, K = 32).
+// Output: X into the group panel buffer, into A in place, and mirrored into the upper tiles (one pass).
+constexpr int TS_ROWS = 64, TS_THREADS = 256, TS_LD = 130;
+constexpr int TS_SMEM = (TS_ROWS * TS_LD + PT * TS_LD) * 8;
+
+struct TrsmTileArgs {
+    double* P; long long lda; long long strideA;      // rows below the tile in A (in/out)
+    const double* Ltile;                              // the tile's factor in A (lower), same lda / strideA
+    const double* Tsub; long long ldt; long long strideT;  // block-diagonal T: 32x32 inverses of the diagonal blocks
+    double* W; long long ldw; long long strideW;      // panel buffer rows (out)
+    double* Aup;                                      // mirror origin: Aup[j * lda + r] = X[r][j]
+    int M, nb, mirror_rows;
+};
+
+__global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTileArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double* Xs = sm;                     // [64][TS_LD]
+    double* Ls = sm + TS_ROWS * TS_LD;   // [128][TS_LD]: L_bc below the diagonal blocks, T_bb on them
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long zb = blockIdx.z;
+    const int r0 = blockIdx.x * TS_ROWS;
+    double* __restrict__ P = a.P + zb * a.strideA;
+    const double* __restrict__ Lt = a.Ltile + zb * a.strideA;
+    const double* __restrict__ Ts = a.Tsub + zb * a.strideT;
+    const int nb = a.nb;
+    const uint32_t xb = smem_u32(Xs), lb = smem_u32(Ls);
+    // stage P rows (16-byte async copies, zero fill beyond M / nb) and the operand tile
+    for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
+        const int r = e >> 6, c = (e & 63) * 2;
+        int bytes = 0;
+        if (r0 + r < a.M) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+        const double* src = bytes ? P + (long long)(r0 + r) * a.lda + c : P;
+        cp_async16(xb + (uint32_t)(r * TS_LD + c) * 8u, src, bytes);
+    }
+    for (int e = tid; e < PT * (PT / 2); e += TS_THREADS) {
+        const int i = e >> 6, c = (e & 63) * 2;
+        const bool diag_blk = (i >> 5) == (c >> 5);
+        if (c > i && !diag_blk) continue;  // blocks above the diagonal blocks are never read
+        int bytes = 0;
+        if (i < nb) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+        const double* src = diag_blk ? Ts + (long long)i * a.ldt + c : Lt + (long long)i * a.lda + c;
+        cp_async16(lb + (uint32_t)(i * TS_LD + c) * 8u, bytes ? src : Lt, bytes);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (nb < PT) {
+        // dead rows / columns of a ragged tile behave like an identity block
+        for (int i = nb + tid; i < PT; i += TS_THREADS) Ls[i * TS_LD + i] = 1.0;
+        __syncthreads();
+    }
+    // the chunk that holds a diagonal entry of T also carries the entry right of it (zero in Tsub): fine.
+    const int gq = lane >> 2, kk = lane & 3;
+    double* xrow = Xs + (warp * 8 + gq) * TS_LD;  // this lane's strip row (A-fragment row and C row)
+    for (int b = 0; b < 4; ++b) {
+        const int cb = 32 * b;
+        double acc[4][2];
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) acc[j8][0] = acc[j8][1] = 0.0;
+        // sum_{k < 32 b} X[i][k] L[cb + j][k]
+        for (int k = 0; k < cb; k += 4) {
+            const double av = xrow[k + kk];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) dmma884(acc[j8][0], acc[j8][1], av, Ls[(cb + 8 * j8 + gq) * TS_LD + k + kk]);
+        }
+        // R = P_b - acc, written back in place (C layout: row gq, columns 2kk, 2kk+1 of each 8-column tile)
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+            xrow[cb + 8 * j8 + 2 * kk] -= acc[j8][0];
+            xrow[cb + 8 * j8 + 2 * kk + 1] -= acc[j8][1];
+            acc[j8][0] = acc[j8][1] = 0.0;
+        }
+        __syncwarp();
+        // X_b = R T_bb^T : sum_k R[i][k] T_bb[j][k]  (T_bb lower: zeros above its diagonal are stored)
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+            const double av = xrow[cb + k + kk];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8)
+                dmma884(acc[j8][0], acc[j8][1], av, Ls[(cb + 8 * j8 + gq) * TS_LD + cb + k + kk]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+            xrow[cb + 8 * j8 + 2 * kk] = acc[j8][0];
+            xrow[cb + 8 * j8 + 2 * kk + 1] = acc[j8][1];
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // write out: panel buffer + A in place (rows of this CTA), then the mirrored upper tiles
+    double* __restrict__ W = a.W + zb * a.strideW;
+    for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
+        const int r = e >> 6, c = (e & 63) * 2;
+        if (r0 + r >= a.M || c >= nb) continue;
+        const double v0 = Xs[r * TS_LD + c], v1 = Xs[r * TS_LD + c + 1];
+        double* wp = W + (long long)(r0 + r) * a.ldw + c;
+        double* ap = P + (long long)(r0 + r) * a.lda + c;
+        if (c + 1 < nb) {
+            *reinterpret_cast<double2*>(wp) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(ap) = make_double2(v0, v1);
+        } else {
+            wp[0] = v0;
+            ap[0] = v0;
+        }
+    }
+    if (a.Aup && r0 < a.mirror_rows) {
+        double* __restrict__ Aup = a.Aup + zb * a.strideA;
+        for (int e = tid; e < PT * TS_ROWS; e += TS_THREADS) {
+            const int j = e >> 6, r = e & 63;  // consecutive threads -> consecutive rows r: contiguous in Aup
+            if (j < nb && r0 + r < a.mirror_rows) Aup[(long long)j * a.lda + r0 + r] = Xs[r * TS_LD + j];
+        }
+    }
+}
+
+static int launch_trsm_tile(const TrsmTileArgs& a, int batch, cudaStream_t stream) {
+    if (a.M <= 0) return GPMP_OK;
+    static unsigned long long configured = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
+        if (cudaFuncSetAttribute(trsm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) !=
+            cudaSuccess)
+            return GPMP_ERR_CUDA;
+        configured |= 1ull << (dev & 63);
+    }
+    LaunchScope scope(KC_GEMM, 2.0 * (double)a.M * PT * PT * batch, stream);
+    dim3 grid(ceil_div(a.M, TS_ROWS), 1, batch);
+    trsm_tile_kernel<<<grid, TS_THREADS, TS_SMEM, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
 }
 
 // ---- panel copy-back: W (rows x nb, ld ldw) -> A panel (lower) and its mirror in the upper tiles --
@@ -511,6 +656,7 @@ struct PotrfCtx {
     double* Tlo; double* Tup; long long strideT;
     int* info; long long strideInfo;
     int batch;
+    double* Tsub;  // optional: 128x128 tile per 128 columns receiving the block-diagonal (32x32) inverses
 };
 
 // Column group [k0, k0+gw) (gw <= NB): 128-wide steps, each = tile factor+inverse, solve of ALL rows below
@@ -531,7 +677,7 @@ static int tile_step(const PotrfCtx& c, int k0, int j0, double* Wg, long long st
     pa.A = c.A + (long long)col * (lda + 1); pa.lda = lda; pa.strideA = c.strideA;
     pa.Tlo = Tlo_k + (long long)j0 * (NB + 1); pa.Tup = Tup_k + (long long)j0 * (NB + 1);
     pa.ldt = NB; pa.strideT = c.strideT; pa.nb = jb; pa.info = c.info; pa.strideInfo = c.strideInfo;
-    pa.row0 = col; pa.dbg = nullptr; pa.invert_only = 0;
+    pa.row0 = col; pa.dbg = nullptr; pa.mode = POTF2_FULL;
     int rc = launch_potf2(pa, c.batch, stream);
     if (rc) return rc;
     const int M = c.nrows - rb;
@@ -549,6 +695,43 @@ static int tile_step(const PotrfCtx& c, int k0, int j0, double* Wg, long long st
     cp.W = Pw; cp.ldw = NB; cp.strideW = strideW; cp.Alo = Pa; cp.Aup = c.A + (long long)col * lda + rb;
     cp.lda = lda; cp.strideA = c.strideA; cp.rows = M; cp.cols = jb; cp.mirror_rows = max(0, c.n - rb);
     return launch_copy_panel(cp, c.batch, stream);
+}
+
+// The chain's version of tile_step: factor-only tile kernel (no 128-wide inverse) and the substitution solve,
+// which also writes A in place and the mirrored tiles (no copy kernel).  The 128-wide inverse of the tile is
+// computed off the chain by tile_inverse().
+static int tile_step_chain(const PotrfCtx& c, int k0, int j0, double* Wg, long long strideW, cudaStream_t stream) {
+    const int NB = c.NB, gw = min(NB, c.n - k0);
+    const long long lda = c.lda;
+    const int jb = min(PT, gw - j0), col = k0 + j0, rb = col + jb;
+    double* Tsub = c.Tsub + (long long)(col / PT) * PT * PT;
+    Potf2Args pa;
+    pa.A = c.A + (long long)col * (lda + 1); pa.lda = lda; pa.strideA = c.strideA;
+    pa.Tlo = Tsub; pa.Tup = nullptr; pa.ldt = PT; pa.strideT = 0; pa.nb = jb;
+    pa.info = c.info; pa.strideInfo = c.strideInfo; pa.row0 = col; pa.dbg = nullptr; pa.mode = POTF2_FACTOR;
+    int rc = launch_potf2(pa, c.batch, stream);
+    if (rc) return rc;
+    const int M = c.nrows - rb;
+    if (M <= 0) return GPMP_OK;
+    TrsmTileArgs t;
+    t.P = c.A + (long long)rb * lda + col; t.lda = lda; t.strideA = c.strideA;
+    t.Ltile = pa.A; t.Tsub = Tsub; t.ldt = PT; t.strideT = 0;
+    t.W = Wg + (long long)(rb - k0) * NB + j0; t.ldw = NB; t.strideW = strideW;
+    t.Aup = c.A + (long long)col * lda + rb; t.M = M; t.nb = jb; t.mirror_rows = max(0, c.n - rb);
+    return launch_trsm_tile(t, c.batch, stream);
+}
+
+// 128-wide inverse of the tile at column `col` from its factor (off the chain).
+static int tile_inverse(const PotrfCtx& c, int k0, int j0, cudaStream_t stream) {
+    const int NB = c.NB, gw = min(NB, c.n - k0);
+    const int jb = min(PT, gw - j0), col = k0 + j0;
+    Potf2Args pa;
+    pa.A = c.A + (long long)col * (c.lda + 1); pa.lda = c.lda; pa.strideA = c.strideA;
+    pa.Tlo = c.Tlo + (long long)(k0 / NB) * NB * NB + (long long)j0 * (NB + 1);
+    pa.Tup = c.Tup + (long long)(k0 / NB) * NB * NB + (long long)j0 * (NB + 1);
+    pa.ldt = NB; pa.strideT = c.strideT; pa.nb = jb; pa.info = nullptr; pa.strideInfo = 0; pa.row0 = col;
+    pa.dbg = nullptr; pa.mode = POTF2_INVERT;
+    return launch_potf2(pa, c.batch, stream);
 }
 
 // K=128 update inside the group starting at k0: the solved step at j0 updates the group's columns
@@ -669,14 +852,14 @@ static LookAhead& lookahead(int nevents) {
 // runs its 128-wide steps, so the latency-bound chain hides behind the big SYRK.
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream) {
+               cudaStream_t stream, double* Tsub) {
     if (n <= 0) return GPMP_OK;
-    PotrfCtx c{A, lda, strideA, n, nrows, NB, Tlo, Tup, strideT, info, strideInfo, batch};
+    PotrfCtx c{A, lda, strideA, n, nrows, NB, Tlo, Tup, strideT, info, strideInfo, batch, Tsub};
     const int nblk = ceil_div(n, NB);
     const long long wrows = nrows > NB ? nrows : NB;
     double* Wb[2] = {W, W + wrows * NB};
     int rc;
-    const bool pipelined = batch == 1 && nblk >= 3 && NB > PT;
+    const bool pipelined = batch == 1 && nblk >= 3 && NB > PT && Tsub != nullptr;
     LookAhead* la = pipelined ? &lookahead(3 + 10 * (nblk + 2)) : nullptr;
     if (!pipelined || !la->ok) {
         for (int k = 0; k < n; k += NB) {
@@ -702,7 +885,7 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
         const int gw = min(NB, n - k0), nblocks = ceil_div(gw, PT);
         for (int cb = 0; cb < nblocks; ++cb) {
             const int j0 = cb * PT;
-            int rc2 = tile_step(c, k0, j0, Wn, strideW, B);
+            int rc2 = tile_step_chain(c, k0, j0, Wn, strideW, B);
             if (rc2) return rc2;
             cudaEventRecord(ev(g, E_TRSM + cb), B);
             if (cb + 1 < nblocks) {
@@ -719,7 +902,13 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
                 rc2 = in_group_update(c, k0, j0, j0 + 2 * PT, gw, Wn, strideW, H);
                 if (rc2) return rc2;
                 cudaEventRecord(ev(g, E_IN + cb), H);
+            } else {
+                cudaStreamWaitEvent(H, ev(g, E_TRSM + cb), 0);
             }
+            // the 128-wide inverse of this tile is needed only after the factorisation: helper stream,
+            // behind the update the chain may be waiting for
+            rc2 = tile_inverse(c, k0, j0, H);
+            if (rc2) return rc2;
         }
         cudaEventRecord(ev(g, E_PANEL), B);
         return GPMP_OK;
@@ -796,7 +985,7 @@ static int launch_copy2d(const double* src, long long lds, double* dst, long lon
 // group's block column of L: row (r - k0) = L[r][k0 .. k0+gw) for r = k0 .. nrows-1 (diagonal tiles included).
 int dist_group(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, int k0, double* panel,
                int* info, cudaStream_t stream) {
-    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1};
+    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1, nullptr};
     int rc = group_panel(c, k0, panel, 0, stream);
     if (rc) return rc;
     const int gw = min(NB, n - k0);
@@ -830,7 +1019,7 @@ int dist_store(double* A, long long lda, int n, int nrows, int NB, int k0, const
 // Every rank: trailing update of the absolute columns [col0, col1) (beyond the group at k0) with its panel.
 int dist_update(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, int col0, int col1,
                 cudaStream_t stream) {
-    PotrfCtx c{A, lda, 0, n, nrows, NB, nullptr, nullptr, 0, nullptr, 0, 1};
+    PotrfCtx c{A, lda, 0, n, nrows, NB, nullptr, nullptr, 0, nullptr, 0, 1, nullptr};
     const int gw = min(NB, n - k0), r0 = k0 + gw;
     if (col0 < r0 || col1 <= col0) return GPMP_ERR_ARG;
     return trailing_update(c, k0, panel + (long long)gw * NB, NB, 0, col0 - r0, col1 - r0, stream);
@@ -847,7 +1036,7 @@ int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo,
         Potf2Args pa;
         pa.A = A + (long long)k0 * (lda + 1); pa.lda = lda; pa.strideA = (long long)PT * (lda + 1);
         pa.Tlo = Tlo_k; pa.Tup = Tup_k; pa.ldt = NB; pa.strideT = (long long)PT * (NB + 1);
-        pa.nb = PT; pa.info = nullptr; pa.strideInfo = 0; pa.row0 = k0; pa.dbg = nullptr; pa.invert_only = 1;
+        pa.nb = PT; pa.info = nullptr; pa.strideInfo = 0; pa.row0 = k0; pa.dbg = nullptr; pa.mode = POTF2_INVERT;
         int rc;
         if (full > 0) {
             rc = launch_potf2(pa, full, stream);
@@ -860,7 +1049,7 @@ int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo,
             if (rc) return rc;
         }
     }
-    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1};
+    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1, nullptr};
     return block_inverses(c, scratch, 0, stream);
 }
 

@@ -418,14 +418,15 @@ def test_edge_shapes_and_inputs(gp):
 
 def test_partitioned_factorisation_matches_local(gp):
     """The panel-partitioned evaluation (owner factors a column group, panel exchange, per-rank updates) run
-    with a single rank must reproduce the local pipeline bit for bit, and leave a state predict can use."""
+    with a single rank must reproduce the local pipeline (to rounding: the local look-ahead path solves its
+    panels by blocked substitution, the partitioned one by the tile inverse) and leave a state predict can use."""
     n, d = 1500, 5
     x, z, xt = cases.data(n, d, 31, m=40)
     th = cases.theta(d, 31)
     m = _model(gp, "linear", 2, False, th)
     v_local = m.negative_log_restricted_likelihood(th, x, z).item()
     v_dist, state = gp.dist.reml_value_distributed(m, th, x, z)
-    assert v_dist == v_local
+    assert relerr(v_dist, v_local) <= 1e-12
     ref = onp.negative_log_restricted_likelihood(
         onp.OracleModel(cases.mean_fn("linear", np), lambda a, b, cp, pw=False: onp.maternp_covariance(a, b, 2, cp, pw),
                         None, th, "linear_predictor"), th, x, z)
