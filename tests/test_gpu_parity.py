@@ -246,6 +246,16 @@ def test_likelihood_not_pd_gives_inf(gp):
     assert torch.isinf(v) and v > 0
     val, grad = gp.num.value_and_grad(lambda t: m.negative_log_restricted_likelihood(t, x, z), th)
     assert torch.isinf(val) and torch.all(grad == 0)
+    # same through the three-stream look-ahead path (n large enough for several column groups)
+    xb = np.random.default_rng(1).uniform(size=(3000, 2))
+    zb = np.sin(xb.sum(1))
+    big = m.negative_log_restricted_likelihood(torch.tensor([-800.0, 0.0, 0.0]), xb, zb)
+    assert torch.isinf(big) and big > 0
+    # and a failure in the middle of a user-composed matrix: one negative diagonal entry at row 1700
+    Kbad = torch.eye(3000, dtype=torch.float64, device="cuda")
+    Kbad[1700, 1700] = -1.0
+    mb = gp.core.Model(cases.mean_fn("const", gp.num), lambda a, b, cp, pairwise=False: Kbad * torch.exp(cp[0]).item())
+    assert torch.isinf(mb.negative_log_restricted_likelihood(torch.tensor([0.0]), xb, zb))
 
 
 def test_reml_selection_example02_end_to_end(gp, golden_t):
