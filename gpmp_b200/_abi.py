@@ -73,6 +73,12 @@ SIGNATURES = {
     "gpmp_lik_dist_store": (_i, [_i, _i, _vp, _sz, _i, _vp, _vp]),
     "gpmp_lik_dist_update": (_i, [_i, _i, _vp, _sz, _i, _vp, _i, _i, _vp]),
     "gpmp_lik_dist_finish": (_i, [_i, _i, _vp, _sz, _vp, _vp, _vp]),
+    "gpmp_lik_ws_offset": (_sz, [_i, _i, _i]),
+    "gpmp_lik_ws_ld": (_ll, [_i]),
+    "gpmp_lik_dist_tup_rows": (_i, [_i, _i, _vp, _sz, _i, _i, _vp]),
+    "gpmp_lik_dist_kinv_rows": (_i, [_i, _i, _vp, _sz, _i, _i, _vp]),
+    "gpmp_lik_dist_u_cols": (_i, [_i, _i, _vp, _sz, _i, _i, _vp]),
+    "gpmp_lik_dist_contract_rows": (_i, [_specp, _vp, _i, _i, _vp, _sz, _i, _i, _vp, _vp]),
     "gpmp_lik_loo": (_i, [_i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "gpmp_predict_scratch_bytes": (_sz, [_i, _i, _i]),
     "gpmp_predict_chunk": (_i, [_specp, _vp, _i, _i, _vp, _sz, _vp, _i, _vp, _vp, _vp, _ll, _vp, _sz, _vp, _vp,

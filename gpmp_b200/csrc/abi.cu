@@ -406,7 +406,7 @@ int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, 
     if (rc) return rc;
     URowsArgs u;
     u.R = A + (long long)n * w.lda; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;
-    u.n = n;
+    u.n = n; u.j0 = 0; u.j1 = 0;
     rc = launch_urows(u, s);
     if (rc) return rc;
     if (spec) {
@@ -429,6 +429,89 @@ int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, 
     return GPMP_OK;
 }
 
+// ---- gradient of the partitioned evaluation: every piece works on one block of rows --------------------
+size_t gpmp_lik_ws_offset(int n, int q, int which) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q) return (size_t)-1;
+    LikWs w = lik_ws(n, q, 1);
+    switch (which) {
+        case 0: return w.off_A;
+        case 1: return w.off_Tup;
+        case 2: return w.off_Kinv;
+        case 3: return w.off_U;
+        case 4: return w.off_Tlo;
+        default: return (size_t)-1;
+    }
+}
+long long gpmp_lik_ws_ld(int n) { return round_ld(n); }
+
+struct DistGradCtx {
+    LikWs w; char* base; double *A, *Tup, *Kinv, *U; const double *Tlo_c, *Tup_c; double* Wsc;
+};
+static int dist_grad_ctx(int n, int q, void* work_dev, size_t work_bytes, int row0, int rows, DistGradCtx* c) {
+    if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || row0 < 0 || rows <= 0 || row0 + rows > n)
+        return GPMP_ERR_ARG;
+    c->w = lik_ws(n, q, 1);
+    if (work_bytes < c->w.off_partial) return GPMP_ERR_WORKSPACE;
+    if (row0 % c->w.pw.NB) return GPMP_ERR_ARG;
+    c->base = static_cast<char*>(work_dev);
+    char* pb = c->base + c->w.off_potrf;
+    c->A = (double*)(c->base + c->w.off_A);
+    c->Tup = (double*)(c->base + c->w.off_Tup);
+    c->Kinv = (double*)(c->base + c->w.off_Kinv);
+    c->U = (double*)(c->base + c->w.off_U);
+    c->Tlo_c = (const double*)(pb + c->w.pw.off_tlo);
+    c->Tup_c = (const double*)(pb + c->w.pw.off_tup);
+    c->Wsc = (double*)(pb + c->w.pw.off_w);
+    return GPMP_OK;
+}
+
+int gpmp_lik_dist_tup_rows(int n, int q, void* work_dev, size_t work_bytes, int row0, int rows, void* stream) {
+    DistGradCtx c;
+    int rc = dist_grad_ctx(n, q, work_dev, work_bytes, row0, rows, &c);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* Bt = c.Tup + (long long)row0 * c.w.lda;
+    rc = launch_unit_rows(Bt, c.w.lda, rows, n, row0, s);
+    if (rc) return rc;
+    return trsm_rows_core(c.A, n, c.w.lda, c.w.pw.NB, c.Tlo_c, c.Tup_c, Bt, rows, c.w.lda, 0, c.Wsc, s,
+                          row0 / c.w.pw.NB);
+}
+
+int gpmp_lik_dist_kinv_rows(int n, int q, void* work_dev, size_t work_bytes, int row0, int rows, void* stream) {
+    DistGradCtx c;
+    int rc = dist_grad_ctx(n, q, work_dev, work_bytes, row0, rows, &c);
+    if (rc) return rc;
+    GemmDesc g = gemm_desc();
+    g.A = c.Tup + (long long)row0 * c.w.lda; g.lda = c.w.lda;
+    g.B = c.Tup; g.ldb = c.w.lda;
+    g.C = c.Kinv + (long long)row0 * c.w.lda; g.ldc = c.w.lda;
+    g.M = rows; g.N = row0 + rows; g.K = n; g.krange = KR_FROM_ROW; g.ktrim_off = row0;
+    return launch_gemm_nt(g, (cudaStream_t)stream);
+}
+
+int gpmp_lik_dist_u_cols(int n, int q, void* work_dev, size_t work_bytes, int row0, int rows, void* stream) {
+    DistGradCtx c;
+    int rc = dist_grad_ctx(n, q, work_dev, work_bytes, row0, rows, &c);
+    if (rc) return rc;
+    URowsArgs u;
+    u.R = c.A + (long long)n * c.w.lda; u.ldr = c.w.lda; u.r = c.w.r; u.Tup = c.Tup; u.ldt = c.w.lda;
+    u.U = c.U; u.ldu = c.w.lda; u.n = n; u.j0 = row0; u.j1 = row0 + rows;
+    return launch_urows(u, (cudaStream_t)stream);
+}
+
+int gpmp_lik_dist_contract_rows(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, void* work_dev,
+                                size_t work_bytes, int row0, int rows, double* grad_dev, void* stream) {
+    if (!spec || !x_dev || !grad_dev) return GPMP_ERR_ARG;
+    DistGradCtx c;
+    int rc = dist_grad_ctx(n, q, work_dev, work_bytes, row0, rows, &c);
+    if (rc) return rc;
+    LikWs w = lik_ws(n, q, spec->d);
+    if (work_bytes < w.total_grad) return GPMP_ERR_WORKSPACE;
+    return launch_contract(spec, x_dev, n, nullptr, n, c.Kinv, w.lda, c.U, w.lda, w.r, 1, 0, 0.5, grad_dev,
+                           c.base + w.off_partial, w.total_grad - w.off_partial, (cudaStream_t)stream, row0 / 64,
+                           (row0 + rows + 63) / 64);
+}
+
 int gpmp_lik_loo(int n, int q, void* work_dev, size_t work_bytes, const double* z_dev, double* zloo_dev,
                  double* s2loo_dev, double* eloo_dev, void* stream) {
     if (n <= 0 || q < 0 || q > GPMP_MAX_Q || !work_dev || !z_dev || !zloo_dev || !s2loo_dev || !eloo_dev)
@@ -448,7 +531,7 @@ int gpmp_lik_loo(int n, int q, void* work_dev, size_t work_bytes, const double* 
     if (rc) return rc;
     URowsArgs u;
     u.R = A + (long long)n * w.lda; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;
-    u.n = n;
+    u.n = n; u.j0 = 0; u.j1 = 0;
     rc = launch_urows(u, s);
     if (rc) return rc;
     return launch_loo(Kinv, w.lda, U, w.lda, q, n, z_dev, zloo_dev, s2loo_dev, eloo_dev, s);

@@ -157,6 +157,8 @@ struct GemmDesc {
     int batch2;
     long long stride2A, stride2B, stride2C, stride2Ct;
     int reverse;  // visit tiles in reverse order (longest-K tiles first for KR_TO_ROW)
+    int ktrim_off;  // added to the tile origin before trimming: the operand is a row / column block of a larger
+                    // triangular matrix that starts ktrim_off rows (columns) further down
 };
 inline GemmDesc gemm_desc() {
     GemmDesc g{};

@@ -93,10 +93,11 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKA
     // of a triangular operand may hold anything outside its diagonal tiles -- e.g. the mirrored other
     // triangle -- so trimming is also what makes the product correct).
     int k0 = 0, k1 = g.K;
-    if (g.krange == KR_FROM_ROW) k0 = min(m0 / KGRAN * KGRAN, g.K);
-    else if (g.krange == KR_TO_ROW) k1 = min(g.K, (m0 / KGRAN + 1) * KGRAN);
-    else if (g.krange == KR_FROM_COL) k0 = min(n0 / KGRAN * KGRAN, g.K);
-    else if (g.krange == KR_TO_COL) k1 = min(g.K, (n0 / KGRAN + 1) * KGRAN);
+    const int mt = m0 + g.ktrim_off, nt = n0 + g.ktrim_off;
+    if (g.krange == KR_FROM_ROW) k0 = min(mt / KGRAN * KGRAN, g.K);
+    else if (g.krange == KR_TO_ROW) k1 = min(g.K, (mt / KGRAN + 1) * KGRAN);
+    else if (g.krange == KR_FROM_COL) k0 = min(nt / KGRAN * KGRAN, g.K);
+    else if (g.krange == KR_TO_COL) k1 = min(g.K, (nt / KGRAN + 1) * KGRAN);
     const int nk = k1 > k0 ? (k1 - k0 + SUBK * BK - 1) / (SUBK * BK) : 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

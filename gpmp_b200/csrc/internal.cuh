@@ -25,7 +25,8 @@ int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batc
 size_t contract_workspace_bytes(int n, int mcols, int d);
 int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const double* y, int mcols, const double* G,
                     long long ldg, const double* Ut, long long ldu, int r, int sym, int dist_only, double half,
-                    double* grad, void* partial, size_t partial_bytes, cudaStream_t stream);
+                    double* grad, void* partial, size_t partial_bytes, cudaStream_t stream, int tile_row0 = 0,
+                    int tile_row1 = -1);
 int launch_pairwise(const gpmp_cov_spec* spec, const double* x, const double* y, int n, double* out, int dist_only,
                     cudaStream_t stream);
 int launch_maternp_elementwise(int p, const double* h, double* k, double* dk, long long count, cudaStream_t stream);
@@ -38,7 +39,8 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
                double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream);
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,
-                   double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream);
+                   double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream,
+                   int first_block = 0);
 
 int dist_group(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, int k0, double* panel,
                int* info, cudaStream_t stream);
@@ -74,6 +76,7 @@ struct URowsArgs {
     const double* Tup; long long ldt;
     double* U; long long ldu;
     int n;
+    int j0, j1;  // columns of U to compute: [j0, j1)  (j1 <= 0: all)
 };
 
 struct DenseGradArgs {
@@ -88,6 +91,7 @@ int launch_logdet_r0(const double* p0rows, double* p0work, long long ld, int n, 
                      cudaStream_t stream);
 int launch_urows(const URowsArgs& a, cudaStream_t stream);
 int launch_dense_grad(const DenseGradArgs& a, cudaStream_t stream);
+int launch_unit_rows(double* B, long long ld, int m, int n, int col0, cudaStream_t stream);
 int launch_loo(const double* Kinv, long long ldk, const double* U, long long ldu, int q, int n, const double* z,
                double* zloo, double* s2loo, double* eloo, cudaStream_t stream);
 

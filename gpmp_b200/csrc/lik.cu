@@ -208,8 +208,8 @@ int launch_finalize(const FinalizeArgs& a, int batch, cudaStream_t stream) {
 constexpr int UR_WARPS = 8;
 __global__ void __launch_bounds__(UR_WARPS * 32) urows_kernel(const URowsArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * UR_WARPS + warp;
-    if (j >= a.n) return;
+    const int j = a.j0 + blockIdx.x * UR_WARPS + warp;
+    if (j >= a.j1) return;
     const double* __restrict__ t = a.Tup + (long long)j * a.ldt;
     for (int a0 = 0; a0 < a.r; a0 += 4) {
         const int cnt = min(4, a.r - a0);
@@ -229,10 +229,14 @@ __global__ void __launch_bounds__(UR_WARPS * 32) urows_kernel(const URowsArgs a)
         }
     }
 }
-int launch_urows(const URowsArgs& a, cudaStream_t stream) {
-    if (a.n <= 0 || a.r <= 0) return GPMP_OK;
+int launch_urows(const URowsArgs& a0, cudaStream_t stream) {
+    if (a0.n <= 0 || a0.r <= 0) return GPMP_OK;
+    URowsArgs a = a0;
+    if (a.j1 <= 0 || a.j1 > a.n) a.j1 = a.n;
+    if (a.j0 < 0) a.j0 = 0;
+    if (a.j0 >= a.j1) return GPMP_OK;
     LaunchScope scope(KC_SMALL, 8.0 * a.n * (a.n + 1.0) / 2.0, stream);
-    urows_kernel<<<ceil_div(a.n, UR_WARPS), UR_WARPS * 32, 0, stream>>>(a);
+    urows_kernel<<<ceil_div(a.j1 - a.j0, UR_WARPS), UR_WARPS * 32, 0, stream>>>(a);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
 }
@@ -260,6 +264,24 @@ int launch_loo(const double* Kinv, long long ldk, const double* U, long long ldu
     LooArgs a{Kinv, ldk, U, ldu, q, n, z, zloo, s2loo, eloo};
     LaunchScope scope(KC_SMALL, 0.0, stream);
     loo_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
+// rows [0, m) of B (ld) <- unit vectors e_{col0 + i}  (right-hand sides of the distributed triangular inverse)
+struct UnitRowsArgs { double* B; long long ld; int m, n, col0; };
+__global__ void unit_rows_kernel(const UnitRowsArgs a) {
+    const int i = blockIdx.y;
+    double* row = a.B + (long long)i * a.ld;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.n; c += gridDim.x * blockDim.x)
+        row[c] = (c == a.col0 + i) ? 1.0 : 0.0;
+}
+int launch_unit_rows(double* B, long long ld, int m, int n, int col0, cudaStream_t stream) {
+    if (m <= 0 || n <= 0) return GPMP_OK;
+    UnitRowsArgs a{B, ld, m, n, col0};
+    LaunchScope scope(KC_SMALL, 0.0, stream);
+    dim3 grid(min(ceil_div(n, 256), 64), m);
+    unit_rows_kernel<<<grid, 256, 0, stream>>>(a);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
 }

@@ -399,6 +399,7 @@ struct ContractArgs {
     const double* Ut; long long ldu; int r;  // optional low-rank correction rows (r x n)
     int n, mcols, sym, same_set, tiles_n;
     int dist_only;    // vjp of the scaled distance itself: weight G_ik / h (0 at h == 0)
+    int tile_off;     // sym mode: index of the first lower tile visited (row-range restricted contraction)
     double* partial;  // [nblocks][2 + d]
 };
 
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
     MaternRegs<P> mr;
     mr.init(&msh);
     int ti, tj;
-    if (a.sym) tri_decode(blockIdx.x, ti, tj);
+    if (a.sym) tri_decode(blockIdx.x + a.tile_off, ti, tj);
     else { ti = blockIdx.x / a.tiles_n; tj = blockIdx.x - ti * a.tiles_n; }
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
     const int r0 = ti * CT, c0 = tj * CT;
@@ -542,7 +543,8 @@ size_t contract_workspace_bytes(int n, int mcols, int d) {
 
 int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const double* y, int mcols, const double* G,
                     long long ldg, const double* Ut, long long ldu, int r, int sym, int dist_only, double half,
-                    double* grad, void* partial, size_t partial_bytes, cudaStream_t stream) {
+                    double* grad, void* partial, size_t partial_bytes, cudaStream_t stream, int tile_row0,
+                    int tile_row1) {
     const bool same = (y == nullptr || y == x);
     if (sym && !same) return GPMP_ERR_ARG;
     if (r > CONTRACT_MAXR) return GPMP_ERR_ARG;
@@ -556,12 +558,20 @@ int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const dou
     const int tm = ceil_div(n, CT), tn = ceil_div(a.mcols, CT);
     a.tiles_n = tn;
     long long nblocks = sym ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
+    a.tile_off = 0;
+    if (sym && (tile_row0 > 0 || tile_row1 >= 0)) {
+        // lower tiles of the tile rows [tile_row0, tile_row1) only (row-partitioned contraction)
+        if (tile_row1 < 0 || tile_row1 > tm) tile_row1 = tm;
+        if (tile_row0 >= tile_row1) tile_row1 = tile_row0;
+        a.tile_off = (int)((long long)tile_row0 * (tile_row0 + 1) / 2);
+        nblocks = (long long)tile_row1 * (tile_row1 + 1) / 2 - a.tile_off;
+    }
     if ((size_t)nblocks * (2 + spec->d) * sizeof(double) > partial_bytes) return GPMP_ERR_WORKSPACE;
     a.partial = static_cast<double*>(partial);
     {
         double bytes = sym ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
         LaunchScope scope(KC_CONTRACT, bytes, stream);
-        switch (dist_only ? 0 : spec->p) {
+        if (nblocks > 0) switch (dist_only ? 0 : spec->p) {
             case 0: contract_kernel<0><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
             case 1: contract_kernel<1><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
             case 2: contract_kernel<2><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;

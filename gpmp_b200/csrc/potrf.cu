@@ -1101,12 +1101,14 @@ int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_
 // trans == 0:  Bt <- Bt L^-T   (forward; uses Tlo diagonal-block inverses and L's lower tiles)
 // trans == 1:  Bt <- Bt L^-1   (backward; uses Tup diagonal-block inverses and the mirrored upper tiles)
 // Block size NB as in the factorisation (complete compact inverses required).  W: m x NB scratch.
+// first_block (trans == 0 only): the right-hand sides are zero left of block first_block, so the forward
+// substitution starts there (unit-vector right-hand sides of the distributed triangular inverse).
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,
-                   double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream) {
+                   double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream, int first_block) {
     if (n <= 0 || m <= 0) return GPMP_OK;
     int rc;
     const int nblk = ceil_div(n, NB);
-    for (int bi = 0; bi < nblk; ++bi) {
+    for (int bi = (trans ? 0 : first_block); bi < nblk; ++bi) {
         const int b = trans ? nblk - 1 - bi : bi;
         const int k = b * NB, nbk = min(NB, n - k);
         const double* T = (trans ? Tup_c : Tlo_c) + (long long)b * NB * NB;

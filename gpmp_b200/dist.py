@@ -46,7 +46,7 @@ def all_gather_rows(local, N, group=None):
     return torch.cat(chunks)
 
 
-def reml_value_distributed(model, covparam, xi, zi, group=None):
+def reml_value_distributed(model, covparam, xi, zi, group=None, want_grad=False):
     """Model.negative_log_restricted_likelihood (value only) with the Cholesky factorisation partitioned over
     the ranks of `group` (BASELINE config 5a).  Returns (value, FitState); every rank gets the same value and
     a complete fitted state (so prediction chunks can be sharded over ranks afterwards)."""
@@ -60,11 +60,34 @@ def reml_value_distributed(model, covparam, xi, zi, group=None):
     with torch.no_grad():
         if fused:
             spec = ops._spec_from_param(K.p, xi_.shape[1], ops.host_values(K.param))
-            state, out = ops.lik_value_dist(spec, None, xi_, zi_, P, group)
+            state, out = ops.lik_value_dist(spec, None, xi_, zi_, P, group, want_grad)
         else:
             Kd = kernel.materialize(K).detach().contiguous()
-            state, out = ops.lik_value_dist(None, Kd, None, zi_, P, group)
+            state, out = ops.lik_value_dist(None, Kd, None, zi_, P, group, want_grad)
     return ops.read_small(out)[0], state
+
+
+def reml_value_and_grad_distributed(model, covparam, xi, zi, group=None):
+    """REML value and covariance-parameter gradient with both the factorisation (column groups) and the
+    gradient's triangular inverse / K^-1 / contraction (row blocks) partitioned over the ranks of `group`.
+    The covariance must be a plain gp.kernel.maternp_covariance (fused path).  Returns (value, grad ndarray),
+    identical on every rank."""
+    import math
+
+    from . import ops
+
+    value, state = reml_value_distributed(model, covparam, xi, zi, group, want_grad=True)
+    nparam = len(ops.host_values(covparam))
+    if not math.isfinite(value):
+        import numpy as np
+
+        return value, np.zeros(nparam)
+    with torch.no_grad():
+        g, _alpha = ops.lik_grad_dist(state, group)
+    vals = ops._expand_iso_grad(ops.read_small(g), nparam, state.d, 1)
+    import numpy as np
+
+    return value, np.asarray(vals)
 
 
 def fit_distributed(model, xi, zi, group=None):

@@ -384,7 +384,7 @@ def lik_value(spec, K, x, z, P, want_grad):
     return FitState(work, n, q, d, spec, x, want_grad), out
 
 
-def lik_value_dist(spec, K, x, z, P, group=None):
+def lik_value_dist(spec, K, x, z, P, group=None, want_grad=False):
     """lik_value with the factorisation partitioned over the ranks of `group` (one process per GPU): column
     groups are owned round-robin, the owner factors a group, the panel is broadcast with NCCL, every rank
     updates the groups it owns.  Every rank ends with the same FitState a local lik_value would leave."""
@@ -396,7 +396,7 @@ def lik_value_dist(spec, K, x, z, P, group=None):
     n = z.shape[0]
     q = 0 if P is None else P.shape[1]
     d = x.shape[1] if x is not None else 1
-    work = _workspace(lib().gpmp_lik_workspace_bytes(n, q, d, 0))
+    work = _workspace(lib().gpmp_lik_workspace_bytes(n, q, d, 1 if want_grad else 0))
     out = _empty((8,))
     info = torch.empty(1, dtype=torch.int32, device=device())
     specp = C.byref(spec) if spec is not None else None
@@ -449,7 +449,63 @@ def lik_value_dist(spec, K, x, z, P, group=None):
         td.all_reduce(info, op=td.ReduceOp.MAX, group=group)
     check(lib().gpmp_lik_dist_finish(n, q, ptr(work), wb, ptr(out), ptr(info), stream_ptr()),
           "gpmp_lik_dist_finish")
-    return FitState(work, n, q, d, spec, x, False), out
+    return FitState(work, n, q, d, spec, x, want_grad), out
+
+
+def _ws_matrix(state, which):
+    """(n x ld) float64 view of a matrix inside a likelihood workspace (0 A, 1 T^T, 2 K^-1, 3 U, 4 T)."""
+    n, q = state.n, state.q
+    off = lib().gpmp_lik_ws_offset(n, q, which)
+    ld = lib().gpmp_lik_ws_ld(n)
+    rows = (q + 1) if which == 3 else n
+    return state.work[off: off + rows * ld * 8].view(torch.float64).view(rows, ld)
+
+
+def lik_grad_dist(state, group=None):
+    """Covariance-parameter gradient (and dvalue/dz) of a state left by lik_value_dist(want_grad=True), with
+    the 2n^3/3 of T = L^-1 and K^-1 split over the ranks by row blocks (owned round-robin like the column
+    groups of the factorisation): T^T rows -> broadcast -> K^-1 rows, U columns -> all-reduce -> contraction of
+    the owned rows -> all-reduce of the 1+d partial sums."""
+    import torch.distributed as td
+
+    from . import dist as gdist
+
+    rank, size = gdist.world(group)
+    n, q, d, spec = state.n, state.q, state.d, state.spec
+    if spec is None:
+        raise _abi.GpmpError("the partitioned gradient needs a Matern covariance spec (fused path)")
+    wb = state.work.numel()
+    NB = lib().gpmp_lik_dist_block(n)
+    blocks = [(r0, min(NB, n - r0)) for r0 in range(0, n, NB)]
+    mine = [b for i, b in enumerate(blocks) if i % size == rank]
+    Tup, U = _ws_matrix(state, 1), _ws_matrix(state, 3)
+    for r0, rows in mine:
+        check(lib().gpmp_lik_dist_tup_rows(n, q, ptr(state.work), wb, r0, rows, stream_ptr()),
+              "gpmp_lik_dist_tup_rows")
+    if size > 1:
+        pend = []
+        for i, (r0, rows) in enumerate(blocks):
+            src = td.get_global_rank(group, i % size) if group is not None else i % size
+            pend.append(td.broadcast(Tup[r0:r0 + rows], src=src, group=group, async_op=True))
+        for h in pend:
+            h.wait()
+    U.zero_()
+    for r0, rows in mine:
+        check(lib().gpmp_lik_dist_kinv_rows(n, q, ptr(state.work), wb, r0, rows, stream_ptr()),
+              "gpmp_lik_dist_kinv_rows")
+        check(lib().gpmp_lik_dist_u_cols(n, q, ptr(state.work), wb, r0, rows, stream_ptr()), "gpmp_lik_dist_u_cols")
+    if size > 1:
+        td.all_reduce(U, op=td.ReduceOp.SUM, group=group)
+    ng = 1 + spec.noise + d
+    total = torch.zeros(ng, dtype=F64, device=device())
+    g = _empty((ng,))
+    for r0, rows in mine:
+        check(lib().gpmp_lik_dist_contract_rows(C.byref(spec), ptr(state.x), n, q, ptr(state.work), wb, r0, rows,
+                                                ptr(g), stream_ptr()), "gpmp_lik_dist_contract_rows")
+        total += g
+    if size > 1:
+        td.all_reduce(total, op=td.ReduceOp.SUM, group=group)
+    return total, U[q, :n].clone()
 
 
 def lik_grad(state, want_dz, want_dK):

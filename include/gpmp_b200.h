@@ -189,6 +189,25 @@ int gpmp_lik_dist_update(int n, int q, void* work_dev, size_t work_bytes, int k0
 int gpmp_lik_dist_finish(int n, int q, void* work_dev, size_t work_bytes, double* out_dev, int* info_dev,
                          void* stream);
 
+/* Gradient of the partitioned evaluation ("gradient contraction K4 -- M rows partitioned,
+ * all-reduce of d+1 doubles").  After gpmp_lik_dist_finish on a workspace sized with want_grad = 1 every rank
+ * holds the full factor; the 2n^3/3 of the gradient is split by blocks of gpmp_lik_dist_block(n) rows:
+ *   gpmp_lik_dist_tup_rows      rows [row0, row0+rows) of T^T = L^-T (unit right-hand sides, forward solve
+ *                               started at their block);  the caller broadcasts those rows to every rank;
+ *   gpmp_lik_dist_kinv_rows     the same rows of K^-1 (columns 0 .. row0+rows) = T^T[rows] (T^T)^T;
+ *   gpmp_lik_dist_u_cols        columns [row0, row0+rows) of U = [Q~^T; r^T] T;  the caller sums U over ranks;
+ *   gpmp_lik_dist_contract_rows 0.5 sum over the lower tiles of those rows of M dK/dtheta -> grad_dev[1+noise+d];
+ *                               the caller sums over its blocks and all-reduces.
+ * gpmp_lik_ws_offset / gpmp_lik_ws_ld locate the matrices inside the workspace (0 A, 1 T^T, 2 K^-1, 3 U, 4 T)
+ * so the caller can hand row blocks to its collective library without copies. */
+size_t gpmp_lik_ws_offset(int n, int q, int which);
+long long gpmp_lik_ws_ld(int n);
+int gpmp_lik_dist_tup_rows(int n, int q, void* work_dev, size_t work_bytes, int row0, int rows, void* stream);
+int gpmp_lik_dist_kinv_rows(int n, int q, void* work_dev, size_t work_bytes, int row0, int rows, void* stream);
+int gpmp_lik_dist_u_cols(int n, int q, void* work_dev, size_t work_bytes, int row0, int rows, void* stream);
+int gpmp_lik_dist_contract_rows(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, void* work_dev,
+                                size_t work_bytes, int row0, int rows, double* grad_dev, void* stream);
+
 /* Leave-one-out predictions by virtual cross-validation (replaces gpmp/core/loo.py:65-130 behind Model.loo,
  * gpmp/core/model.py:309-343) after gpmp_lik_value on a workspace sized with want_grad = 1 and the (centred)
  * data z_dev that was whitened:  eloo_i = (Pi z)_i / Pi_ii,  s2loo_i = 1 / Pi_ii,  zloo_i = z_i - eloo_i, with

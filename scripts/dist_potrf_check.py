@@ -45,7 +45,33 @@ for _ in range(2):
         m.negative_log_restricted_likelihood(th, xd, zd)
     torch.cuda.synchronize()
     t_local.append(time.perf_counter() - t0)
-# predict a few points from the distributed state on every rank and compare across ranks
+# gradient: partitioned vs local autograd
+tp = torch.tensor(th, requires_grad=True)
+v_loc = m.negative_log_restricted_likelihood(tp, xd, zd)
+(g_loc,) = torch.autograd.grad(v_loc, tp)
+vg, gd = gp.dist.reml_value_and_grad_distributed(m, th, xd, zd)
+tg = []
+for _ in range(2):
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    vg, gd = gp.dist.reml_value_and_grad_distributed(m, th, xd, zd)
+    torch.cuda.synchronize()
+    tg.append(time.perf_counter() - t0)
+tl = []
+for _ in range(2):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tp = torch.tensor(th, requires_grad=True)
+    v_loc = m.negative_log_restricted_likelihood(tp, xd, zd)
+    (g_loc,) = torch.autograd.grad(v_loc, tp)
+    torch.cuda.synchronize()
+    tl.append(time.perf_counter() - t0)
+grad_rel = float(np.max(np.abs(gd - g_loc.numpy())) / np.max(np.abs(g_loc.numpy())))
+if rank == 0:
+    print(json.dumps({"grad_rel_dist_vs_local": grad_rel, "t_value_grad_dist_s": min(tg), "t_value_grad_local_s": min(tl),
+                      "tflops_vg_dist": float(n) ** 3 / min(tg) / 1e12, "tflops_vg_local": float(n) ** 3 / min(tl) / 1e12}))
 if rank == 0:
     print(json.dumps({"n": n, "world": world, "value_local": v1, "value_dist": vd, "rel": abs(vd - v1) / abs(v1),
                       "t_dist_s": min(ts), "t_local_s": min(t_local),

@@ -444,6 +444,11 @@ def test_partitioned_factorisation_matches_local(gp):
     mean, var = gp.dist.predict_distributed(m, x, z, xt)
     mean1, var1 = m.predict(x, z, xt)
     assert np.array_equal(mean, mean1) and np.array_equal(var, var1)
+    # the row-partitioned gradient (T^T rows, K^-1 rows, contraction of the owned rows) against autograd
+    tp = torch.tensor(th, requires_grad=True)
+    (g_local,) = torch.autograd.grad(m.negative_log_restricted_likelihood(tp, x, z), tp)
+    v2, g_dist = gp.dist.reml_value_and_grad_distributed(m, th, x, z)
+    assert relerr(v2, v_local) <= 1e-12 and relerr_norm(g_dist, g_local.numpy()) <= 1e-10
     m.covparam = th
     fitted = gp.dist.fit_distributed(m, x, z)
     mean2, var2 = gp.dist.predict_distributed(m, x, z, xt, fitted=fitted)
