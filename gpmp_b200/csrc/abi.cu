@@ -608,7 +608,7 @@ int gpmp_lik_trsm_rows(int n, int q, void* work_dev, size_t work_bytes, double* 
 struct BatchWs {
     int n, q, r, nrows, NB, nblk;
     long long lda;
-    size_t per_A, per_T, per_W, per_mdev, per_particle;
+    size_t per_A, per_T, per_W, per_mdev, per_tsub, per_particle;
     size_t shared;  // p0rows + p0work + ldr0 + dummy out
 };
 static BatchWs batch_ws(int n, int q) {
@@ -621,7 +621,8 @@ static BatchWs batch_ws(int n, int q) {
     w.per_T = align_up((size_t)w.nblk * w.NB * w.NB * 8, 256);
     w.per_W = align_up((size_t)2 * (w.nrows > w.NB ? w.nrows : w.NB) * w.NB * 8, 256);
     w.per_mdev = align_up(sizeof(MaternDev), 256);
-    w.per_particle = w.per_A + 2 * w.per_T + w.per_W + w.per_mdev;
+    w.per_tsub = 128 * 128 * 8;
+    w.per_particle = w.per_A + 2 * w.per_T + w.per_W + w.per_mdev + w.per_tsub;
     w.shared = 2 * align_up((size_t)(q > 0 ? q : 1) * w.lda * 8, 256) + 256 + 256;
     return w;
 }
@@ -655,6 +656,7 @@ int gpmp_criterion_batched(const gpmp_cov_spec* spec, const double* theta_dev, i
     double* Tup = (double*)(pbase + (size_t)cap * (w.per_A + w.per_T));
     double* W = (double*)(pbase + (size_t)cap * (w.per_A + 2 * w.per_T));
     MaternDev* mdev = (MaternDev*)(pbase + (size_t)cap * (w.per_A + 2 * w.per_T + w.per_W));
+    double* Tsub = (double*)(pbase + (size_t)cap * (w.per_A + 2 * w.per_T + w.per_W + w.per_mdev));
     const long long sA = (long long)(w.per_A / 8), sT = (long long)(w.per_T / 8), sW = (long long)(w.per_W / 8);
     int rc;
     if (cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)N, s) != cudaSuccess) return GPMP_ERR_CUDA;
@@ -672,7 +674,8 @@ int gpmp_criterion_batched(const gpmp_cov_spec* spec, const double* theta_dev, i
         lr.p0rows = (q > 0 && c0 == 0) ? p0rows : nullptr; lr.ld0 = w.lda;
         rc = launch_load_rows(lr, nb, s);
         if (rc) return rc;
-        rc = potrf_core(A, w.lda, sA, n, w.nrows, w.NB, Tlo, Tup, sT, W, sW, info_dev + c0, 1, nb, s);
+        rc = potrf_core(A, w.lda, sA, n, w.nrows, w.NB, Tlo, Tup, sT, W, sW, info_dev + c0, 1, nb, s, Tsub,
+                        (long long)(w.per_tsub / 8));
         if (rc) return rc;
         FinalizeArgs f;
         f.rows = lr.rows; f.ld = w.lda; f.strideRows = sA;

@@ -35,7 +35,7 @@ int launch_maternp_elementwise(int p, const double* h, double* k, double* dk, lo
 int potrf_block_size(int n);
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream, double* Tsub = nullptr);
+               cudaStream_t stream, double* Tsub = nullptr, long long strideTsub = 0);
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
                double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream);
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,

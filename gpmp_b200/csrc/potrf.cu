@@ -657,6 +657,7 @@ struct PotrfCtx {
     int* info; long long strideInfo;
     int batch;
     double* Tsub;  // optional: 128x128 tile per 128 columns receiving the block-diagonal (32x32) inverses
+    long long strideTsub;  // batched: ONE such tile per batch entry, reused by every step (value-only path)
 };
 
 // Column group [k0, k0+gw) (gw <= NB): 128-wide steps, each = tile factor+inverse, solve of ALL rows below
@@ -704,10 +705,10 @@ static int tile_step_chain(const PotrfCtx& c, int k0, int j0, double* Wg, long l
     const int NB = c.NB, gw = min(NB, c.n - k0);
     const long long lda = c.lda;
     const int jb = min(PT, gw - j0), col = k0 + j0, rb = col + jb;
-    double* Tsub = c.Tsub + (long long)(col / PT) * PT * PT;
+    double* Tsub = c.batch > 1 ? c.Tsub : c.Tsub + (long long)(col / PT) * PT * PT;
     Potf2Args pa;
     pa.A = c.A + (long long)col * (lda + 1); pa.lda = lda; pa.strideA = c.strideA;
-    pa.Tlo = Tsub; pa.Tup = nullptr; pa.ldt = PT; pa.strideT = 0; pa.nb = jb;
+    pa.Tlo = Tsub; pa.Tup = nullptr; pa.ldt = PT; pa.strideT = c.strideTsub; pa.nb = jb;
     pa.info = c.info; pa.strideInfo = c.strideInfo; pa.row0 = col; pa.dbg = nullptr; pa.mode = POTF2_FACTOR;
     int rc = launch_potf2(pa, c.batch, stream);
     if (rc) return rc;
@@ -715,9 +716,10 @@ static int tile_step_chain(const PotrfCtx& c, int k0, int j0, double* Wg, long l
     if (M <= 0) return GPMP_OK;
     TrsmTileArgs t;
     t.P = c.A + (long long)rb * lda + col; t.lda = lda; t.strideA = c.strideA;
-    t.Ltile = pa.A; t.Tsub = Tsub; t.ldt = PT; t.strideT = 0;
+    t.Ltile = pa.A; t.Tsub = Tsub; t.ldt = PT; t.strideT = c.strideTsub;
     t.W = Wg + (long long)(rb - k0) * NB + j0; t.ldw = NB; t.strideW = strideW;
-    t.Aup = c.A + (long long)col * lda + rb; t.M = M; t.nb = jb; t.mirror_rows = max(0, c.n - rb);
+    t.Aup = c.batch > 1 ? nullptr : c.A + (long long)col * lda + rb;  // batched values need no mirrored tiles
+    t.M = M; t.nb = jb; t.mirror_rows = max(0, c.n - rb);
     return launch_trsm_tile(t, c.batch, stream);
 }
 
@@ -755,8 +757,11 @@ static int in_group_update(const PotrfCtx& c, int k0, int j0, int c0, int c1, do
 // Whole group on one stream (the non-pipelined path).
 static int group_panel(const PotrfCtx& c, int k0, double* Wg, long long strideW, cudaStream_t stream) {
     const int gw = min(c.NB, c.n - k0);
+    // batched value-only evaluations (Tsub given, batch > 1) never need the 128-wide inverses: factor-only
+    // tile kernel + substitution solve
+    const bool light = c.batch > 1 && c.Tsub != nullptr;
     for (int j0 = 0; j0 < gw; j0 += PT) {
-        int rc = tile_step(c, k0, j0, Wg, strideW, stream);
+        int rc = light ? tile_step_chain(c, k0, j0, Wg, strideW, stream) : tile_step(c, k0, j0, Wg, strideW, stream);
         if (rc) return rc;
         rc = in_group_update(c, k0, j0, j0 + PT, gw, Wg, strideW, stream);
         if (rc) return rc;
@@ -769,6 +774,7 @@ static int group_panel(const PotrfCtx& c, int k0, double* Wg, long long strideW,
 static int block_inverses(const PotrfCtx& c, double* Xscr, long long strideX, cudaStream_t stream) {
     const int NB = c.NB, n = c.n;
     if (NB <= PT) return GPMP_OK;
+    if (c.batch > 1 && c.Tsub != nullptr) return GPMP_OK;  // value-only batched path: no tile inverses exist
     const int nfull = n / NB, rem = n - nfull * NB;
     int rc;
     for (int s = PT; s < NB; s *= 2) {
@@ -852,9 +858,9 @@ static LookAhead& lookahead(int nevents) {
 // runs its 128-wide steps, so the latency-bound chain hides behind the big SYRK.
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream, double* Tsub) {
+               cudaStream_t stream, double* Tsub, long long strideTsub) {
     if (n <= 0) return GPMP_OK;
-    PotrfCtx c{A, lda, strideA, n, nrows, NB, Tlo, Tup, strideT, info, strideInfo, batch, Tsub};
+    PotrfCtx c{A, lda, strideA, n, nrows, NB, Tlo, Tup, strideT, info, strideInfo, batch, Tsub, strideTsub};
     const int nblk = ceil_div(n, NB);
     const long long wrows = nrows > NB ? nrows : NB;
     double* Wb[2] = {W, W + wrows * NB};
@@ -985,7 +991,7 @@ static int launch_copy2d(const double* src, long long lds, double* dst, long lon
 // group's block column of L: row (r - k0) = L[r][k0 .. k0+gw) for r = k0 .. nrows-1 (diagonal tiles included).
 int dist_group(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, int k0, double* panel,
                int* info, cudaStream_t stream) {
-    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1, nullptr};
+    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1, nullptr, 0};
     int rc = group_panel(c, k0, panel, 0, stream);
     if (rc) return rc;
     const int gw = min(NB, n - k0);
@@ -1019,7 +1025,7 @@ int dist_store(double* A, long long lda, int n, int nrows, int NB, int k0, const
 // Every rank: trailing update of the absolute columns [col0, col1) (beyond the group at k0) with its panel.
 int dist_update(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, int col0, int col1,
                 cudaStream_t stream) {
-    PotrfCtx c{A, lda, 0, n, nrows, NB, nullptr, nullptr, 0, nullptr, 0, 1, nullptr};
+    PotrfCtx c{A, lda, 0, n, nrows, NB, nullptr, nullptr, 0, nullptr, 0, 1, nullptr, 0};
     const int gw = min(NB, n - k0), r0 = k0 + gw;
     if (col0 < r0 || col1 <= col0) return GPMP_ERR_ARG;
     return trailing_update(c, k0, panel + (long long)gw * NB, NB, 0, col0 - r0, col1 - r0, stream);
@@ -1049,7 +1055,7 @@ int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo,
             if (rc) return rc;
         }
     }
-    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1, nullptr};
+    PotrfCtx c{A, lda, 0, n, nrows, NB, Tlo, Tup, 0, info, 0, 1, nullptr, 0};
     return block_inverses(c, scratch, 0, stream);
 }
 
