@@ -184,17 +184,44 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
                 }
                 __syncwarp();
                 if (o < 24) {
-                    // rank-8 update of the rest of the block (lower 8x8 tiles) on the tensor pipe
+                    // rank-8 update of the rest of the block (lower 8x8 tiles, at most 3 x 3) on the tensor
+                    // pipe: all fragments first (3 row strips serve both operands), then the independent
+                    // DMMAs, then the read-modify-writes -- one latency each instead of one per tile
                     const double* Px = D + (o + 8) * PLD + o;
                     double* Cx = D + (o + 8) * PLD + o + 8;
                     const int m8 = (24 - o) / 8;
-                    smem_mma<8>(
-                        m8, m8, 0, 1, [&](int i, int k) { return Px[i * PLD + k]; },
-                        [&](int j, int k) { return Px[j * PLD + k]; }, [&](int i8, int j8) { return j8 <= i8; },
-                        [&](int i, int j, double c0v, double c1v) {
-                            if (j <= i) Cx[i * PLD + j] -= c0v;
-                            if (j + 1 <= i) Cx[i * PLD + j + 1] -= c1v;
-                        });
+                    const int gq = lane >> 2, kk = lane & 3;
+                    double f0[3], f1[3];
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const bool on = t < m8;
+                        f0[t] = on ? Px[(t * 8 + gq) * PLD + kk] : 0.0;
+                        f1[t] = on ? Px[(t * 8 + gq) * PLD + 4 + kk] : 0.0;
+                    }
+                    double acc[6][2];
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+                    for (int i8 = 0; i8 < 3; ++i8)
+#pragma unroll
+                        for (int j8 = 0; j8 <= i8; ++j8) {
+                            const int t = i8 * (i8 + 1) / 2 + j8;
+                            if (i8 < m8) {  // warp-uniform
+                                dmma884(acc[t][0], acc[t][1], f0[i8], f0[j8]);
+                                dmma884(acc[t][0], acc[t][1], f1[i8], f1[j8]);
+                            }
+                        }
+#pragma unroll
+                    for (int i8 = 0; i8 < 3; ++i8)
+#pragma unroll
+                        for (int j8 = 0; j8 <= i8; ++j8) {
+                            const int t = i8 * (i8 + 1) / 2 + j8;
+                            if (i8 < m8) {
+                                const int i = i8 * 8 + gq, j = j8 * 8 + 2 * kk;
+                                if (j <= i) Cx[i * PLD + j] -= acc[t][0];
+                                if (j + 1 <= i) Cx[i * PLD + j + 1] -= acc[t][1];
+                            }
+                        }
                 }
                 __syncwarp();
             }
