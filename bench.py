@@ -17,8 +17,9 @@ value    : device-resident inputs (x, z already in HBM); theta (9 doubles) goes 
 e2e      : the same K steps through the public API with HOST numpy inputs: x, z and theta are copied
            host->device inside the timed region every step, value and gradient are read back.
 roofline : FP64 tensor (DMMA) pipe.  achieved = n^3 flop per evaluation (potrf n^3/3 + trtri n^3/3 +
-           lauum n^3/3) / time spent in the DMMA GEMM kernel per evaluation, measured with
-           CUDA events around every launch on the launching stream in a second pass over the same K steps.
+           lauum n^3/3) / step time -- a lower bound of the DMMA GEMM's rate, because its launches
+           overlap on three streams; the per-launch CUDA-event sums (second pass over the same K steps, events
+           on each launching stream) are reported per kernel class beside it.
 """
 from __future__ import annotations
 
@@ -241,7 +242,11 @@ def run_gpu(args):
     _abi.prof_enable(False)
     flops = float(N_OBS) ** 3
     gemm_ms = prof["dmma_gemm"]["ms_per_step"]
-    achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    gemm_event_sum_tflops = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # The DMMA GEMM launches of one step overlap on three streams (bulk / chain / helper), so their event times
+    # sum to MORE than the step; n^3 / step time is therefore a lower bound of the kernel's rate and is what is
+    # reported as `achieved` (the event-sum figure is kept beside it).
+    achieved = flops / (ms * 1e-3 / args.steps) / 1e12
 
     if rank != 0:
         if world > 1:
@@ -270,7 +275,9 @@ def run_gpu(args):
         "peak_source": "nominal HGX B200 FP64 (MEASURED_PEAKS.json has no fp64 entry); cuBLAS dgemm 4096^3 "
                        f"measured in this run: {cublas_tf:.1f} TFLOP/s",
         "algorithmic_flops_per_step": flops,
-        "whole_step_tflops": flops / (ms * 1e-3 / args.steps) / 1e12,
+        "achieved_basis": "n^3 flop / step time: lower bound of the kernel's rate (its launches overlap on three "
+                          "streams, so per-launch CUDA-event times sum to more than the step)",
+        "gemm_event_sum_tflops": gemm_event_sum_tflops,
         "per_class": prof,
     }
 
