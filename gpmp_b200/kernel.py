@@ -119,3 +119,20 @@ def maternp_covariance(x, y, p, param, pairwise=False):
     if y is x or y is None:
         return maternp_covariance_ii_or_tt(x, p, param, pairwise)
     return maternp_covariance_it(x, y, p, param, pairwise)
+
+
+# parameter selection front-ends live in gpmp.kernel in the reference (kernel/__init__.py); same names here
+from .selection import (  # noqa: E402,F401
+    anisotropic_parameters_initial_guess,
+    anisotropic_parameters_initial_guess_constant_mean,
+    anisotropic_parameters_initial_guess_zero_mean,
+    autoselect_parameters,
+    make_selection_criterion_with_gradient,
+    negative_log_likelihood,
+    negative_log_likelihood_zero_mean,
+    negative_log_restricted_likelihood,
+    select_parameters_with_criterion,
+    select_parameters_with_ml,
+    select_parameters_with_ml_zero_mean,
+    select_parameters_with_reml,
+)

@@ -284,6 +284,14 @@ def test_reml_selection_example02_end_to_end(gp, golden_t):
     assert r.success
     assert abs(best["J"] - float(g["fun"])) <= 1e-6 * max(1.0, abs(float(g["fun"])))
     assert np.max(np.abs(best["p"] - g["covparam"])) <= 1e-3
+    # the packaged driver (initial guess + SLSQP) must retrace the reference's run: same start, same optimum
+    m2 = gp.core.Model(cases.mean_fn("const", gp.num),
+                       lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, p, cp, pairwise))
+    m2, info = gp.kernel.select_parameters_with_reml(m2, x, z, info=True)
+    assert np.max(np.abs(info["covparam0"] - th0)) <= 1e-8 * max(1.0, np.max(np.abs(th0)))
+    assert abs(float(info.fun) - float(g["fun"])) <= 1e-6 * max(1.0, abs(float(g["fun"])))
+    assert np.max(np.abs(np.asarray(m2.covparam) - g["covparam"])) <= 1e-3
+    assert callable(info["selection_criterion_nograd"]) and np.isfinite(float(info.selection_criterion_nograd(g["covparam"])))
     m.covparam = g["covparam"]  # predict at the reference's parameters: isolates the predictor from the optimiser
     mean, var = m.predict(x, z, xt)
     s2 = float(np.exp(g["covparam"][0]))
