@@ -134,7 +134,7 @@ __device__ __forceinline__ double block_sum(double v, double* red /* >= 33 doubl
     return red[32];
 }
 
-static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------

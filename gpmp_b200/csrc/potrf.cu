@@ -458,12 +458,22 @@ int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int*
 }
 
 // ---- panel solve by blocked substitution (the chain's solve: needs only the 32x32 block inverses) ---------
-// X = P L^-T for the rows below a 128-wide tile: 64 rows per CTA, one 8-row strip per warp.  Rows are
+// X = P L^-T for the rows below a 128-wide tile, in blocks of 64 rows, one 8-row strip per warp.  Rows are
 // independent, so after the operands are staged every warp walks its strip through the four 32-column block
 // steps on its own:  R_b = P_b - sum_{c<b} X_c L_bc^T  (DMMA, K = 32 b),  X_b = R_b T_bb^T  (DMMA, K = 32).
+// A CTA stages the operand tile once (lower block rows only, packed) and then walks `blocks_per_cta`
+// consecutive row blocks with the next block's rows in flight (cp.async, two buffers) while the current one is
+// solved: the chain launches one block per CTA (latency), batched evaluations one CTA per matrix (throughput).
 // Output: X into the group panel buffer, into A in place, and mirrored into the upper tiles (one pass).
-constexpr int TS_ROWS = 64, TS_THREADS = 256, TS_LD = 130;
-constexpr int TS_SMEM = (TS_ROWS * TS_LD + PT * TS_LD) * 8;
+// Batched value-only runs also pass the few extra (whitening) rows of the matrix separately: a ninth warp solves
+// them as one more strip and every block then applies  E[:, rows] -= X_E X_rows^T  itself, so neither this solve
+// nor the trailing update carries a ragged 2-row tile per matrix.
+constexpr int TS_ROWS = 64, TS_THREADS = 288, TS_LD = 132;  // 132 = 4 mod 16: conflict-free DMMA fragments
+constexpr int TS_LP = 10752;  // packed operand: block row b (32 rows) keeps 32 (b + 1) columns, ld 32 b + 36
+constexpr int TS_EXTRA = 8;   // extra rows the kernel can carry (one strip)
+constexpr int TS_SMEM = (TS_LP + 2 * TS_ROWS * TS_LD + TS_EXTRA * TS_LD) * 8;
+__device__ __forceinline__ int ts_ld(int b) { return 32 * b + 36; }
+__device__ __forceinline__ int ts_base(int b) { return 512 * b * (b - 1) + 1152 * b; }
 
 struct TrsmTileArgs {
     double* P; long long lda; long long strideA;      // rows below the tile in A (in/out)
@@ -472,111 +482,197 @@ struct TrsmTileArgs {
     double* W; long long ldw; long long strideW;      // panel buffer rows (out)
     double* Aup;                                      // mirror origin: Aup[j * lda + r] = X[r][j]
     int M, nb, mirror_rows;
+    int blocks_per_cta;   // consecutive 64-row blocks walked by one CTA
+    int inplace_from;     // rows below this index are not written back into A (value-only batched runs need
+                          // only the panel buffer for them)
+    double* E;            // optional extra rows at the tile's columns (E[i * lda + c], same strideA): solved in
+    int nextra;           // place; their columns right of the tile (E + nb + r) receive -X_E X_r^T for every row r
 };
 
 __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTileArgs a) {
     extern __shared__ __align__(16) double sm[];
-    double* Xs = sm;                     // [64][TS_LD]
-    double* Ls = sm + TS_ROWS * TS_LD;   // [128][TS_LD]: L_bc below the diagonal blocks, T_bb on them
+    double* Lp = sm;                     // packed operand: L_bc below the diagonal blocks, T_bb on them
+    double* Xbuf = sm + TS_LP;           // two buffers of [64][TS_LD]
+    double* Es = Xbuf + 2 * TS_ROWS * TS_LD;  // [8][TS_LD]: the extra rows' strip
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long zb = blockIdx.z;
-    const int r0 = blockIdx.x * TS_ROWS;
     double* __restrict__ P = a.P + zb * a.strideA;
     const double* __restrict__ Lt = a.Ltile + zb * a.strideA;
     const double* __restrict__ Ts = a.Tsub + zb * a.strideT;
+    double* __restrict__ W = a.W + zb * a.strideW;
     const int nb = a.nb;
-    const uint32_t xb = smem_u32(Xs), lb = smem_u32(Ls);
-    // stage P rows (16-byte async copies, zero fill beyond M / nb) and the operand tile
-    for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
-        const int r = e >> 6, c = (e & 63) * 2;
-        int bytes = 0;
-        if (r0 + r < a.M) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
-        const double* src = bytes ? P + (long long)(r0 + r) * a.lda + c : P;
-        cp_async16(xb + (uint32_t)(r * TS_LD + c) * 8u, src, bytes);
+    const int blk0 = blockIdx.x * a.blocks_per_cta;
+    const int nextra = a.E ? a.nextra : 0;
+    double* __restrict__ E = a.E ? a.E + zb * a.strideA : nullptr;
+    int nblocks = min(a.blocks_per_cta, ceil_div(a.M, TS_ROWS) - blk0);
+    if (nblocks <= 0) {
+        if (nextra == 0 || blockIdx.x != 0) return;
+        nblocks = 1;  // no rows below the tile: one pass for the extra rows only
     }
-    for (int e = tid; e < PT * (PT / 2); e += TS_THREADS) {
-        const int i = e >> 6, c = (e & 63) * 2;
-        const bool diag_blk = (i >> 5) == (c >> 5);
-        if (c > i && !diag_blk) continue;  // blocks above the diagonal blocks are never read
-        int bytes = 0;
-        if (i < nb) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
-        const double* src = diag_blk ? Ts + (long long)i * a.ldt + c : Lt + (long long)i * a.lda + c;
-        cp_async16(lb + (uint32_t)(i * TS_LD + c) * 8u, bytes ? src : Lt, bytes);
+    // stage the rows of one block (16-byte async copies, zero fill beyond M / nb)
+    auto stage_rows = [&](int blk, int buf) {
+        const uint32_t xb = smem_u32(Xbuf + buf * TS_ROWS * TS_LD);
+        const int r0 = blk * TS_ROWS;
+        for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            int bytes = 0;
+            if (r0 + r < a.M) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+            const double* src = bytes ? P + (long long)(r0 + r) * a.lda + c : P;
+            cp_async16(xb + (uint32_t)(r * TS_LD + c) * 8u, src, bytes);
+        }
+    };
+    {
+        const uint32_t lb = smem_u32(Lp);
+        for (int e = tid; e < PT * (PT / 2); e += TS_THREADS) {
+            const int i = e >> 6, c = (e & 63) * 2;
+            const int b = i >> 5;
+            if (c >= 32 * (b + 1)) continue;  // blocks above the diagonal blocks are never read
+            const bool diag_blk = (c >> 5) == b;
+            int bytes = 0;
+            if (i < nb) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+            const double* src = diag_blk ? Ts + (long long)i * a.ldt + c : Lt + (long long)i * a.lda + c;
+            cp_async16(lb + (uint32_t)(ts_base(b) + (i - 32 * b) * ts_ld(b) + c) * 8u, bytes ? src : Lt, bytes);
+        }
     }
+    if (nextra) {
+        const uint32_t eb = smem_u32(Es);
+        for (int e = tid; e < TS_EXTRA * (PT / 2); e += TS_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            int bytes = 0;
+            if (r < nextra) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+            cp_async16(eb + (uint32_t)(r * TS_LD + c) * 8u, bytes ? E + (long long)r * a.lda + c : E, bytes);
+        }
+    }
+    stage_rows(blk0, 0);
     cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    if (nb < PT) {
-        // dead rows / columns of a ragged tile behave like an identity block
-        for (int i = nb + tid; i < PT; i += TS_THREADS) Ls[i * TS_LD + i] = 1.0;
-        __syncthreads();
-    }
     // the chunk that holds a diagonal entry of T also carries the entry right of it (zero in Tsub): fine.
     const int gq = lane >> 2, kk = lane & 3;
-    double* xrow = Xs + (warp * 8 + gq) * TS_LD;  // this lane's strip row (A-fragment row and C row)
-    for (int b = 0; b < 4; ++b) {
-        const int cb = 32 * b;
-        double acc[4][2];
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) acc[j8][0] = acc[j8][1] = 0.0;
-        // sum_{k < 32 b} X[i][k] L[cb + j][k]
-        for (int k = 0; k < cb; k += 4) {
-            const double av = xrow[k + kk];
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) dmma884(acc[j8][0], acc[j8][1], av, Ls[(cb + 8 * j8 + gq) * TS_LD + k + kk]);
-        }
-        // R = P_b - acc, written back in place (C layout: row gq, columns 2kk, 2kk+1 of each 8-column tile)
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-            xrow[cb + 8 * j8 + 2 * kk] -= acc[j8][0];
-            xrow[cb + 8 * j8 + 2 * kk + 1] -= acc[j8][1];
-            acc[j8][0] = acc[j8][1] = 0.0;
-        }
-        __syncwarp();
-        // X_b = R T_bb^T : sum_k R[i][k] T_bb[j][k]  (T_bb lower: zeros above its diagonal are stored)
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-            const double av = xrow[cb + k + kk];
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8)
-                dmma884(acc[j8][0], acc[j8][1], av, Ls[(cb + 8 * j8 + gq) * TS_LD + cb + k + kk]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-            xrow[cb + 8 * j8 + 2 * kk] = acc[j8][0];
-            xrow[cb + 8 * j8 + 2 * kk + 1] = acc[j8][1];
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    // write out: panel buffer + A in place (rows of this CTA), then the mirrored upper tiles
-    double* __restrict__ W = a.W + zb * a.strideW;
-    for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
-        const int r = e >> 6, c = (e & 63) * 2;
-        if (r0 + r >= a.M || c >= nb) continue;
-        const double v0 = Xs[r * TS_LD + c], v1 = Xs[r * TS_LD + c + 1];
-        double* wp = W + (long long)(r0 + r) * a.ldw + c;
-        double* ap = P + (long long)(r0 + r) * a.lda + c;
-        if (c + 1 < nb) {
-            *reinterpret_cast<double2*>(wp) = make_double2(v0, v1);
-            *reinterpret_cast<double2*>(ap) = make_double2(v0, v1);
+    for (int it = 0; it < nblocks; ++it) {
+        const int r0 = (blk0 + it) * TS_ROWS;
+        double* Xs = Xbuf + (it & 1) * TS_ROWS * TS_LD;
+        if (it + 1 < nblocks) {
+            stage_rows(blk0 + it + 1, (it + 1) & 1);
+            cp_async_commit();
+            cp_async_wait<1>();
         } else {
-            wp[0] = v0;
-            ap[0] = v0;
+            cp_async_wait<0>();
         }
-    }
-    if (a.Aup && r0 < a.mirror_rows) {
-        double* __restrict__ Aup = a.Aup + zb * a.strideA;
-        for (int e = tid; e < PT * TS_ROWS; e += TS_THREADS) {
-            const int j = e >> 6, r = e & 63;  // consecutive threads -> consecutive rows r: contiguous in Aup
-            if (j < nb && r0 + r < a.mirror_rows) Aup[(long long)j * a.lda + r0 + r] = Xs[r * TS_LD + j];
+        __syncthreads();
+        if (it == 0 && nb < PT) {
+            // dead rows / columns of a ragged tile behave like an identity block
+            for (int i = nb + tid; i < PT; i += TS_THREADS) {
+                const int b = i >> 5;
+                Lp[ts_base(b) + (i - 32 * b) * ts_ld(b) + i] = 1.0;
+            }
+            __syncthreads();
         }
+        // this lane's strip row (A-fragment row and C row); the ninth warp owns the extra rows' strip
+        double* xrow = warp < 8 ? Xs + (warp * 8 + gq) * TS_LD : Es + gq * TS_LD;
+        const bool active = warp < 8 || (it == 0 && nextra > 0);
+        for (int b = 0; b < (active ? 4 : 0); ++b) {
+            const int cb = 32 * b, ldb = ts_ld(b);
+            const double* Lb = Lp + ts_base(b) + gq * ldb + kk;  // + 8 j8 ldb + k
+            double acc[4][2];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) acc[j8][0] = acc[j8][1] = 0.0;
+            // sum_{k < 32 b} X[i][k] L[cb + j][k]
+            for (int k0 = 0; k0 < cb; k0 += 32) {
+                // 32 columns per round: all fragments first, then the 32 DMMAs (four independent chains)
+                double av[8], bv[8][4];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    av[s] = xrow[k0 + 4 * s + kk];
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) bv[s][j8] = Lb[8 * j8 * ldb + k0 + 4 * s];
+                }
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) dmma884(acc[j8][0], acc[j8][1], av[s], bv[s][j8]);
+            }
+            // R = P_b - acc, written back in place (C layout: row gq, columns 2kk, 2kk+1 of each 8-column tile)
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+                xrow[cb + 8 * j8 + 2 * kk] -= acc[j8][0];
+                xrow[cb + 8 * j8 + 2 * kk + 1] -= acc[j8][1];
+                acc[j8][0] = acc[j8][1] = 0.0;
+            }
+            __syncwarp();
+            // X_b = R T_bb^T : sum_k R[i][k] T_bb[j][k]  (T_bb lower: zeros above its diagonal are stored)
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+                const double av = xrow[cb + k + kk];
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) dmma884(acc[j8][0], acc[j8][1], av, Lb[8 * j8 * ldb + cb + k]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+                xrow[cb + 8 * j8 + 2 * kk] = acc[j8][0];
+                xrow[cb + 8 * j8 + 2 * kk + 1] = acc[j8][1];
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // write out: panel buffer + A in place (rows of this block), then the mirrored upper tiles
+        for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            if (r0 + r >= a.M || c >= nb) continue;
+            const double v0 = Xs[r * TS_LD + c], v1 = Xs[r * TS_LD + c + 1];
+            double* wp = W + (long long)(r0 + r) * a.ldw + c;
+            double* ap = P + (long long)(r0 + r) * a.lda + c;
+            const bool inplace = r0 + r >= a.inplace_from;
+            if (c + 1 < nb) {
+                *reinterpret_cast<double2*>(wp) = make_double2(v0, v1);
+                if (inplace) *reinterpret_cast<double2*>(ap) = make_double2(v0, v1);
+            } else {
+                wp[0] = v0;
+                if (inplace) ap[0] = v0;
+            }
+        }
+        if (a.Aup && r0 < a.mirror_rows) {
+            double* __restrict__ Aup = a.Aup + zb * a.strideA;
+            for (int e = tid; e < PT * TS_ROWS; e += TS_THREADS) {
+                const int j = e >> 6, r = e & 63;  // consecutive threads -> consecutive rows r: contiguous in Aup
+                if (j < nb && r0 + r < a.mirror_rows) Aup[(long long)j * a.lda + r0 + r] = Xs[r * TS_LD + j];
+            }
+        }
+        if (nextra) {
+            // extra rows: their part right of the tile, columns of this block:  E[i][nb + r0 + r] -= X_E[i] . X[r]
+            // (k rotated by r: neighbouring rows read different banks of both operands)
+            for (int o = tid; o < nextra * TS_ROWS; o += TS_THREADS) {
+                const int i = o >> 6, r = o & 63;
+                if (r0 + r >= a.M) continue;
+                const double* er = Es + i * TS_LD;
+                const double* xr = Xs + r * TS_LD;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+                for (int j = 0; j < PT; j += 4) {
+                    const int k0 = (j + r) & (PT - 1), k1 = (j + 1 + r) & (PT - 1), k2 = (j + 2 + r) & (PT - 1),
+                              k3 = (j + 3 + r) & (PT - 1);
+                    s0 = fma(er[k0], xr[k0], s0);
+                    s1 = fma(er[k1], xr[k1], s1);
+                    s2 = fma(er[k2], xr[k2], s2);
+                    s3 = fma(er[k3], xr[k3], s3);
+                }
+                E[(long long)i * a.lda + nb + r0 + r] -= (s0 + s1) + (s2 + s3);
+            }
+            if (it == 0 && blockIdx.x == 0) {
+                // the solved extra rows themselves, in place
+                for (int e = tid; e < nextra * PT; e += TS_THREADS) {
+                    const int i = e >> 7, c = e & (PT - 1);
+                    if (c < nb) E[(long long)i * a.lda + c] = Es[i * TS_LD + c];
+                }
+            }
+        }
+        __syncthreads();  // the buffer is refilled by the prefetch of the next iteration
     }
 }
 
-static int launch_trsm_tile(const TrsmTileArgs& a, int batch, cudaStream_t stream) {
-    if (a.M <= 0) return GPMP_OK;
+static int launch_trsm_tile(TrsmTileArgs a, int batch, cudaStream_t stream) {
+    if (a.M < 0) a.M = 0;
+    if (a.E == nullptr) a.nextra = 0;
+    if (a.M <= 0 && a.nextra <= 0) return GPMP_OK;
     static unsigned long long configured = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -587,7 +683,12 @@ static int launch_trsm_tile(const TrsmTileArgs& a, int batch, cudaStream_t strea
         configured |= 1ull << (dev & 63);
     }
     LaunchScope scope(KC_GEMM, 2.0 * (double)a.M * PT * PT * batch, stream);
-    dim3 grid(ceil_div(a.M, TS_ROWS), 1, batch);
+    // enough CTAs for two per SM (148 SMs); beyond that every CTA walks several row blocks of its matrix
+    const int nblocks = max(1, ceil_div(a.M, TS_ROWS));
+    // (one CTA per matrix when it carries extra rows: it rewrites them in place)
+    const int splits = a.nextra > 0 ? 1 : min(nblocks, max(1, ceil_div(2 * 148, batch)));
+    a.blocks_per_cta = ceil_div(nblocks, splits);
+    dim3 grid(ceil_div(nblocks, a.blocks_per_cta), 1, batch);
     trsm_tile_kernel<<<grid, TS_THREADS, TS_SMEM, stream>>>(a);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
@@ -685,6 +786,8 @@ struct PotrfCtx {
     int batch;
     double* Tsub;  // optional: 128x128 tile per 128 columns receiving the block-diagonal (32x32) inverses
     long long strideTsub;  // batched: ONE such tile per batch entry, reused by every step (value-only path)
+    int nextra;    // > 0: rows n .. n + nextra - 1 of A ride through the panel solves as the solve kernel's extra
+                   // strip (batched value-only path); nrows == n then
 };
 
 // Column group [k0, k0+gw) (gw <= NB): 128-wide steps, each = tile factor+inverse, solve of ALL rows below
@@ -740,13 +843,16 @@ static int tile_step_chain(const PotrfCtx& c, int k0, int j0, double* Wg, long l
     int rc = launch_potf2(pa, c.batch, stream);
     if (rc) return rc;
     const int M = c.nrows - rb;
-    if (M <= 0) return GPMP_OK;
+    if (M <= 0 && c.nextra == 0) return GPMP_OK;
     TrsmTileArgs t;
+    t.E = c.nextra ? c.A + (long long)c.n * lda + col : nullptr; t.nextra = c.nextra;
     t.P = c.A + (long long)rb * lda + col; t.lda = lda; t.strideA = c.strideA;
     t.Ltile = pa.A; t.Tsub = Tsub; t.ldt = PT; t.strideT = c.strideTsub;
     t.W = Wg + (long long)(rb - k0) * NB + j0; t.ldw = NB; t.strideW = strideW;
     t.Aup = c.batch > 1 ? nullptr : c.A + (long long)col * lda + rb;  // batched values need no mirrored tiles
     t.M = M; t.nb = jb; t.mirror_rows = max(0, c.n - rb);
+    t.blocks_per_cta = 1;
+    t.inplace_from = c.batch > 1 ? max(0, c.n - rb) : 0;  // batched values: only the extra rows are read back from A
     return launch_trsm_tile(t, c.batch, stream);
 }
 
@@ -887,7 +993,10 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
                cudaStream_t stream, double* Tsub, long long strideTsub) {
     if (n <= 0) return GPMP_OK;
-    PotrfCtx c{A, lda, strideA, n, nrows, NB, Tlo, Tup, strideT, info, strideInfo, batch, Tsub, strideTsub};
+    // batched value-only runs: the few whitening rows below the matrix travel as the solve kernel's extra strip
+    const int nextra = (batch > 1 && Tsub != nullptr && nrows > n && nrows - n <= TS_EXTRA) ? nrows - n : 0;
+    if (nextra) nrows = n;
+    PotrfCtx c{A, lda, strideA, n, nrows, NB, Tlo, Tup, strideT, info, strideInfo, batch, Tsub, strideTsub, nextra};
     const int nblk = ceil_div(n, NB);
     const long long wrows = nrows > NB ? nrows : NB;
     double* Wb[2] = {W, W + wrows * NB};
