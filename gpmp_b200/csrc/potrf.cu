@@ -28,6 +28,15 @@ constexpr int PLD = 130;         // smem leading dimension of the tile (even: ro
 constexpr int XLD = 66;          // smem leading dimension of the scratch
 constexpr int POTF2_THREADS = 512;
 constexpr int POTF2_SMEM = (PT * PLD + 96 * XLD + PT) * 8;
+// Packed lower tile: block row b (32 rows) keeps its 32 (b + 1) leading columns with leading dimension
+// 32 b + 36 (= 4 mod 16: conflict-free DMMA fragment loads); 10752 doubles instead of 128 x 130.
+constexpr int TS_LP = 10752;
+__device__ __forceinline__ int ts_ld(int b) { return 32 * b + 36; }
+__device__ __forceinline__ int ts_base(int b) { return 512 * b * (b - 1) + 1152 * b; }
+__device__ __forceinline__ int pk(int r, int c) {
+    const int b = r >> 5;
+    return ts_base(b) + (r - 32 * b) * ts_ld(b) + c;
+}
 
 struct Potf2Args {
     double* A; long long lda; long long strideA;      // tile origin (diagonal position), in/out
@@ -432,6 +441,279 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
     POTF2_STAMP(18);
 }
 
+
+// ---- factor-only tile kernel (the chain's and the batched sweeps' version) ----------------------------------
+// Same arithmetic as potf2_kernel in POTF2_FACTOR mode (factor + the four 32x32 diagonal-block inverses), but
+// the tile is kept packed (lower block rows only, 84 KB) and the CTA has 8 warps, so two tiles share an SM:
+// a batched sweep overlaps the serial pivot chain of one tile with the tensor-pipe phases of the other.
+constexpr int PF_THREADS = 256;
+constexpr int PF_XLD = 20;
+constexpr int PF_SMEM = (TS_LP + 4 * 16 * PF_XLD + PT) * 8;
+
+__global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2Args a) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                       // packed tile: lower = L, strict upper of the diagonal blocks = T_bb^T
+    double* X = sm + TS_LP;               // per-warp 16 x 16 scratch of the block inversion
+    double* rinv = X + 4 * 16 * PF_XLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PF_THREADS / 32;
+    const long long zb = blockIdx.x;
+    double* __restrict__ A = a.A + zb * a.strideA;
+    const int nb = a.nb;
+    {
+        const uint32_t sb = smem_u32(S);
+        for (int e = tid; e < PT * (PT / 2); e += PF_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;  // chunk of two columns
+            if (c > r) continue;
+            int bytes = 0;
+            if (r < nb) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+            const double* src = bytes ? A + (long long)r * a.lda + c : A;
+            cp_async16(sb + (uint32_t)pk(r, c) * 8u, src, bytes);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // strict upper part of the diagonal blocks (the chunk holding the diagonal keeps its first entry)
+        for (int e = tid; e < PT * 16; e += PF_THREADS) {
+            const int r = e >> 4, c = (r & ~31) + (e & 15) * 2;
+            if (c + 1 <= r) continue;
+            if (c > r) S[pk(r, c)] = 0.0;
+            S[pk(r, c + 1)] = 0.0;
+        }
+        if (tid >= nb && tid < PT) S[pk(tid, tid)] = 1.0;
+    }
+    __syncthreads();
+
+    int bad = 0;  // 1-based local index of the first non-positive pivot (warp 0, lane 0 only)
+    for (int jb = 0; jb < 4; ++jb) {
+        const int c0 = jb * 32, ldd = ts_ld(jb);
+        double* D = S + pk(c0, c0);  // diagonal block: rows share the leading dimension ldd
+        if (warp == 0) {
+            for (int sb = 0; sb < 4; ++sb) {
+                const int o = sb * 8;
+                if (lane == 0) {
+                    // 8x8 diagonal block: the pivot chain, entirely in registers
+                    double m[8][8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) m[i][j] = D[(o + i) * ldd + o + j];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double piv = m[j][j];
+                        if (!(piv > 0.0) && bad == 0) bad = c0 + o + j + 1;
+                        const double ri = fast_rsqrt(piv);
+                        m[j][j] = piv * ri;
+                        rinv[c0 + o + j] = ri;
+#pragma unroll
+                        for (int i = j + 1; i < 8; ++i) m[i][j] *= ri;
+#pragma unroll
+                        for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+                            for (int k = j + 1; k <= i; ++k) m[i][k] = fma(-m[i][j], m[k][j], m[i][k]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) D[(o + i) * ldd + o + j] = m[i][j];
+                }
+                __syncwarp();
+                if (lane >= o + 8) {
+                    // rows of the block below the 8x8: x = p L8^-T, one row per lane
+                    double xr[8];
+                    double* myrow = D + lane * ldd;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) xr[t] = myrow[o + t];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        xr[t] *= rinv[c0 + o + t];
+#pragma unroll
+                        for (int u = t + 1; u < 8; ++u) xr[u] = fma(-xr[t], D[(o + u) * ldd + o + t], xr[u]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) myrow[o + t] = xr[t];
+                }
+                __syncwarp();
+                if (o < 24) {
+                    // rank-8 update of the rest of the block (lower 8x8 tiles, at most 3 x 3) on the tensor
+                    // pipe: all fragments first, then the independent DMMAs, then the read-modify-writes
+                    const double* Px = D + (o + 8) * ldd + o;
+                    double* Cx = D + (o + 8) * ldd + o + 8;
+                    const int m8 = (24 - o) / 8;
+                    const int gq = lane >> 2, kk = lane & 3;
+                    double f0[3], f1[3];
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const bool on = t < m8;
+                        f0[t] = on ? Px[(t * 8 + gq) * ldd + kk] : 0.0;
+                        f1[t] = on ? Px[(t * 8 + gq) * ldd + 4 + kk] : 0.0;
+                    }
+                    double acc[6][2];
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+                    for (int i8 = 0; i8 < 3; ++i8)
+#pragma unroll
+                        for (int j8 = 0; j8 <= i8; ++j8) {
+                            const int t = i8 * (i8 + 1) / 2 + j8;
+                            if (i8 < m8) {  // warp-uniform
+                                dmma884(acc[t][0], acc[t][1], f0[i8], f0[j8]);
+                                dmma884(acc[t][0], acc[t][1], f1[i8], f1[j8]);
+                            }
+                        }
+#pragma unroll
+                    for (int i8 = 0; i8 < 3; ++i8)
+#pragma unroll
+                        for (int j8 = 0; j8 <= i8; ++j8) {
+                            const int t = i8 * (i8 + 1) / 2 + j8;
+                            if (i8 < m8) {
+                                const int i = i8 * 8 + gq, j = j8 * 8 + 2 * kk;
+                                if (j <= i) Cx[i * ldd + j] -= acc[t][0];
+                                if (j + 1 <= i) Cx[i * ldd + j + 1] -= acc[t][1];
+                            }
+                        }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        const int rb = c0 + 32;       // first row below the diagonal block
+        const int mrows = PT - rb;    // rows below
+        if (mrows > 0) {
+            // rows below: x = p Ld^-T by forward substitution, one thread per row (Ld broadcast from smem)
+            if (tid < mrows) {
+                double* prow = S + pk(rb + tid, c0);
+                double x[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) x[k] = prow[k];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    x[k] *= rinv[c0 + k];
+#pragma unroll
+                    for (int j = k + 1; j < 32; ++j) x[j] = fma(-x[k], D[j * ldd + k], x[j]);
+                }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) prow[k] = x[k];
+            }
+            __syncthreads();
+            // trailing update of the lower 8x8 tiles: S[rb.., rb..] -= P P^T, P = S[rb.., c0..c0+32)
+            smem_mma<32>(
+                mrows / 8, mrows / 8, warp, nwarps, [&](int i, int k) { return S[pk(rb + i, c0 + k)]; },
+                [&](int j, int k) { return S[pk(rb + j, c0 + k)]; }, [&](int i8, int j8) { return j8 <= i8; },
+                [&](int i, int j, double c0v, double c1v) {
+                    // diagonal 8x8 tiles: touch the lower part only (the upper part is reserved for T^T)
+                    double* cp = S + pk(rb + i, rb + j);
+                    if (j <= i) cp[0] -= c0v;
+                    if (j + 1 <= i) cp[1] -= c1v;
+                });
+            __syncthreads();
+        }
+    }
+    if (warp == 0 && lane == 0 && bad && a.info) {
+        int* ip = a.info + zb * a.strideInfo;
+        atomicCAS(ip, 0, a.row0 + bad);
+    }
+
+    // ---- inverse of the four 32x32 diagonal blocks, one warp each: 8x8 in registers, then 8 -> 16 -> 32 ---
+    if (warp < 4) {
+        const int c0 = warp * 32, ldd = ts_ld(warp);
+        double* D = S + pk(c0, c0);
+        const double* rv = rinv + c0;
+        // T(i,k) of this block (block coordinates); T_ik (i > k) is kept at D[k][i]
+        auto Tg = [&](int i, int k) -> double { return i > k ? D[k * ldd + i] : (i == k ? rv[i] : 0.0); };
+        double* Xw = X + warp * 16 * PF_XLD;  // per-warp scratch (16 x 16)
+        if (lane < 4) {
+            const int q0 = 8 * lane;
+            double l[8][8], t[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j) l[i][j] = D[(q0 + i) * ldd + q0 + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                t[j][j] = rv[q0 + j];
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = j; k < i; ++k) acc = fma(l[i][k], t[k][j], acc);
+                    t[i][j] = -acc * rv[q0 + i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j) D[(q0 + j) * ldd + q0 + i] = t[i][j];
+        }
+        __syncwarp();
+        // s = 8: pairs (0,1) and (2,3) of 8-blocks
+        for (int pr = 0; pr < 2; ++pr) {
+            const int a0 = 16 * pr, b0 = a0 + 8;
+            smem_mma<8>(
+                1, 1, 0, 1, [&](int i, int k) { return D[(b0 + i) * ldd + a0 + k]; },
+                [&](int j, int k) { return Tg(a0 + k, a0 + j); }, [&](int, int) { return true; },
+                [&](int i, int j, double c0v, double c1v) {
+                    Xw[(8 * pr + i) * PF_XLD + j] = c0v;
+                    Xw[(8 * pr + i) * PF_XLD + j + 1] = c1v;
+                });
+        }
+        __syncwarp();
+        for (int pr = 0; pr < 2; ++pr) {
+            const int a0 = 16 * pr, b0 = a0 + 8;
+            smem_mma<8>(
+                1, 1, 0, 1, [&](int i, int k) { return Tg(b0 + i, b0 + k); },
+                [&](int j, int k) { return Xw[(8 * pr + k) * PF_XLD + j]; }, [&](int, int) { return true; },
+                [&](int i, int j, double c0v, double c1v) {
+                    D[(a0 + j) * ldd + b0 + i] = -c0v;
+                    D[(a0 + j + 1) * ldd + b0 + i] = -c1v;
+                });
+        }
+        __syncwarp();
+        // s = 16
+        smem_mma<16>(
+            2, 2, 0, 1, [&](int i, int k) { return D[(16 + i) * ldd + k]; },
+            [&](int j, int k) { return Tg(k, j); }, [&](int, int) { return true; },
+            [&](int i, int j, double c0v, double c1v) {
+                Xw[i * PF_XLD + j] = c0v;
+                Xw[i * PF_XLD + j + 1] = c1v;
+            });
+        __syncwarp();
+        smem_mma<16>(
+            2, 2, 0, 1, [&](int i, int k) { return Tg(16 + i, 16 + k); },
+            [&](int j, int k) { return Xw[k * PF_XLD + j]; }, [&](int, int) { return true; },
+            [&](int i, int j, double c0v, double c1v) {
+                D[j * ldd + 16 + i] = -c0v;
+                D[(j + 1) * ldd + 16 + i] = -c1v;
+            });
+    }
+    __syncthreads();
+
+    // ---- write back: L (lower, zero upper) into A; the diagonal blocks of T into Tlo ------------------------
+    const bool vec = ((a.lda & 1) == 0) && ((a.ldt & 1) == 0);
+    for (int e = tid; e < PT * (PT / 2); e += PF_THREADS) {
+        const int r = e >> 6, c = (e & 63) * 2;
+        if (r >= nb || c >= nb) continue;
+        const double l0 = c <= r ? S[pk(r, c)] : 0.0;
+        const double l1 = c + 1 <= r ? S[pk(r, c + 1)] : 0.0;
+        double* dst = A + (long long)r * a.lda + c;
+        if (vec && c + 1 < nb) *reinterpret_cast<double2*>(dst) = make_double2(l0, l1);
+        else {
+            dst[0] = l0;
+            if (c + 1 < nb) dst[1] = l1;
+        }
+        if (a.Tlo && (r >> 5) == (c >> 5)) {
+            // T[r][c] (r > c, same diagonal block) lives at S[c][r]
+            double* __restrict__ Tlo = a.Tlo + zb * a.strideT + (long long)r * a.ldt + c;
+            const double t0 = r > c ? S[pk(c, r)] : (r == c ? rinv[r] : 0.0);
+            const double t1 = r > c + 1 ? S[pk(c + 1, r)] : (r == c + 1 ? rinv[r] : 0.0);
+            if (vec && c + 1 < nb) *reinterpret_cast<double2*>(Tlo) = make_double2(t0, t1);
+            else {
+                Tlo[0] = t0;
+                if (c + 1 < nb) Tlo[1] = t1;
+            }
+        }
+    }
+}
+
 static int launch_potf2(const Potf2Args& a, int batch, cudaStream_t stream) {
     static unsigned long long configured = 0;  // one bit per device: the attribute is per context
     int dev = 0;
@@ -443,6 +725,19 @@ static int launch_potf2(const Potf2Args& a, int batch, cudaStream_t stream) {
         configured |= 1ull << (dev & 63);
     }
     LaunchScope scope(KC_POTF2, (double)batch * (PT * (double)PT * PT), stream);  // n^3/3 + 2n^3/3
+    // more tiles than SMs: the packed 8-warp kernel (two tiles per SM); otherwise the 16-warp kernel (latency)
+    if (a.mode == POTF2_FACTOR && batch > 148) {
+        static unsigned long long configured_f = 0;
+        if (!((configured_f >> (dev & 63)) & 1ull)) {
+            if (cudaFuncSetAttribute(potf2_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM) !=
+                cudaSuccess)
+                return GPMP_ERR_CUDA;
+            configured_f |= 1ull << (dev & 63);
+        }
+        potf2_factor_kernel<<<batch, PF_THREADS, PF_SMEM, stream>>>(a);
+        GPMP_CHECK_LAUNCH();
+        return GPMP_OK;
+    }
     potf2_kernel<<<batch, POTF2_THREADS, POTF2_SMEM, stream>>>(a);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
@@ -469,11 +764,8 @@ int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int*
 // them as one more strip and every block then applies  E[:, rows] -= X_E X_rows^T  itself, so neither this solve
 // nor the trailing update carries a ragged 2-row tile per matrix.
 constexpr int TS_ROWS = 64, TS_THREADS = 288, TS_LD = 132;  // 132 = 4 mod 16: conflict-free DMMA fragments
-constexpr int TS_LP = 10752;  // packed operand: block row b (32 rows) keeps 32 (b + 1) columns, ld 32 b + 36
 constexpr int TS_EXTRA = 8;   // extra rows the kernel can carry (one strip)
 constexpr int TS_SMEM = (TS_LP + 2 * TS_ROWS * TS_LD + TS_EXTRA * TS_LD) * 8;
-__device__ __forceinline__ int ts_ld(int b) { return 32 * b + 36; }
-__device__ __forceinline__ int ts_base(int b) { return 512 * b * (b - 1) + 1152 * b; }
 
 struct TrsmTileArgs {
     double* P; long long lda; long long strideA;      // rows below the tile in A (in/out)
@@ -639,23 +931,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
         }
         if (nextra) {
             // extra rows: their part right of the tile, columns of this block:  E[i][nb + r0 + r] -= X_E[i] . X[r]
-            // (k rotated by r: neighbouring rows read different banks of both operands)
-            for (int o = tid; o < nextra * TS_ROWS; o += TS_THREADS) {
-                const int i = o >> 6, r = o & 63;
-                if (r0 + r >= a.M) continue;
-                const double* er = Es + i * TS_LD;
-                const double* xr = Xs + r * TS_LD;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-                for (int j = 0; j < PT; j += 4) {
-                    const int k0 = (j + r) & (PT - 1), k1 = (j + 1 + r) & (PT - 1), k2 = (j + 2 + r) & (PT - 1),
-                              k3 = (j + 3 + r) & (PT - 1);
-                    s0 = fma(er[k0], xr[k0], s0);
-                    s1 = fma(er[k1], xr[k1], s1);
-                    s2 = fma(er[k2], xr[k2], s2);
-                    s3 = fma(er[k3], xr[k3], s3);
+            // one 8x8 output tile per warp (rows = extra rows, columns = the warp's own strip), K = 128 on DMMA
+            if (warp < 8 && r0 + warp * 8 < a.M) {
+                const double* er = Es + gq * TS_LD + kk;
+                const double* xr = Xs + (warp * 8 + gq) * TS_LD + kk;
+                double c[4][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < PT; k0 += 32) {
+                    double av[8], bv[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { av[q] = er[k0 + 4 * q]; bv[q] = xr[k0 + 4 * q]; }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dmma884(c[q & 3][0], c[q & 3][1], av[q], bv[q]);
                 }
-                E[(long long)i * a.lda + nb + r0 + r] -= (s0 + s1) + (s2 + s3);
+                const double s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+                const double s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+                const int r = warp * 8 + 2 * kk;
+                if (gq < nextra) {
+                    double* ep = E + (long long)gq * a.lda + nb + r0 + r;
+                    if (r0 + r < a.M) ep[0] -= s0;
+                    if (r0 + r + 1 < a.M) ep[1] -= s1;
+                }
             }
             if (it == 0 && blockIdx.x == 0) {
                 // the solved extra rows themselves, in place
