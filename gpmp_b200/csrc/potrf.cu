@@ -757,13 +757,14 @@ int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int*
 // independent, so after the operands are staged every warp walks its strip through the four 32-column block
 // steps on its own:  R_b = P_b - sum_{c<b} X_c L_bc^T  (DMMA, K = 32 b),  X_b = R_b T_bb^T  (DMMA, K = 32).
 // A CTA stages the operand tile once (lower block rows only, packed) and then walks `blocks_per_cta`
-// consecutive row blocks with the next block's rows in flight (cp.async, two buffers) while the current one is
-// solved: the chain launches one block per CTA (latency), batched evaluations one CTA per matrix (throughput).
+// consecutive row blocks with its two halves (8 warps, one buffer and one named barrier each) taking alternate
+// blocks independently, so the load / store phases of one half overlap the tensor-pipe phase of the other:
+// the chain launches one block per CTA (latency), batched evaluations one CTA per matrix (throughput).
 // Output: X into the group panel buffer, into A in place, and mirrored into the upper tiles (one pass).
-// Batched value-only runs also pass the few extra (whitening) rows of the matrix separately: a ninth warp solves
-// them as one more strip and every block then applies  E[:, rows] -= X_E X_rows^T  itself, so neither this solve
-// nor the trailing update carries a ragged 2-row tile per matrix.
-constexpr int TS_ROWS = 64, TS_THREADS = 288, TS_LD = 132;  // 132 = 4 mod 16: conflict-free DMMA fragments
+// Batched value-only runs also pass the few extra (whitening) rows of the matrix separately: a seventeenth warp
+// solves them as one more strip and every block then applies  E[:, rows] -= X_E X_rows^T  itself, so neither this
+// solve nor the trailing update carries a ragged 2-row tile per matrix.
+constexpr int TS_ROWS = 64, TS_HALF_THREADS = 256, TS_THREADS = 2 * TS_HALF_THREADS + 32, TS_LD = 132;  // 132 = 4 mod 16: conflict-free DMMA fragments
 constexpr int TS_EXTRA = 8;   // extra rows the kernel can carry (one strip)
 constexpr int TS_SMEM = (TS_LP + 2 * TS_ROWS * TS_LD + TS_EXTRA * TS_LD) * 8;
 
@@ -781,12 +782,17 @@ struct TrsmTileArgs {
     int nextra;           // place; their columns right of the tile (E + nb + r) receive -X_E X_r^T for every row r
 };
 
+__device__ __forceinline__ void half_barrier(int half) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(TS_HALF_THREADS) : "memory");
+}
+
 __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTileArgs a) {
     extern __shared__ __align__(16) double sm[];
     double* Lp = sm;                     // packed operand: L_bc below the diagonal blocks, T_bb on them
-    double* Xbuf = sm + TS_LP;           // two buffers of [64][TS_LD]
+    double* Xbuf = sm + TS_LP;           // one buffer of [64][TS_LD] per half
     double* Es = Xbuf + 2 * TS_ROWS * TS_LD;  // [8][TS_LD]: the extra rows' strip
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp >> 3, hw = warp & 7, htid = tid & (TS_HALF_THREADS - 1);  // warp 16: half == 2
     const long long zb = blockIdx.z;
     double* __restrict__ P = a.P + zb * a.strideA;
     const double* __restrict__ Lt = a.Ltile + zb * a.strideA;
@@ -801,11 +807,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
         if (nextra == 0 || blockIdx.x != 0) return;
         nblocks = 1;  // no rows below the tile: one pass for the extra rows only
     }
-    // stage the rows of one block (16-byte async copies, zero fill beyond M / nb)
-    auto stage_rows = [&](int blk, int buf) {
-        const uint32_t xb = smem_u32(Xbuf + buf * TS_ROWS * TS_LD);
+    double* Xs = Xbuf + (half & 1) * TS_ROWS * TS_LD;
+    // stage the rows of one block into this half's buffer (16-byte async copies, zero fill beyond M / nb)
+    auto stage_rows = [&](int blk) {
+        const uint32_t xb = smem_u32(Xs);
         const int r0 = blk * TS_ROWS;
-        for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
+        for (int e = htid; e < TS_ROWS * (PT / 2); e += TS_HALF_THREADS) {
             const int r = e >> 6, c = (e & 63) * 2;
             int bytes = 0;
             if (r0 + r < a.M) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
@@ -835,33 +842,23 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
             cp_async16(eb + (uint32_t)(r * TS_LD + c) * 8u, bytes ? E + (long long)r * a.lda + c : E, bytes);
         }
     }
-    stage_rows(blk0, 0);
+    if (half < 2 && half < nblocks) stage_rows(blk0 + half);
     cp_async_commit();
-    // the chunk that holds a diagonal entry of T also carries the entry right of it (zero in Tsub): fine.
-    const int gq = lane >> 2, kk = lane & 3;
-    for (int it = 0; it < nblocks; ++it) {
-        const int r0 = (blk0 + it) * TS_ROWS;
-        double* Xs = Xbuf + (it & 1) * TS_ROWS * TS_LD;
-        if (it + 1 < nblocks) {
-            stage_rows(blk0 + it + 1, (it + 1) & 1);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (nb < PT) {
+        // dead rows / columns of a ragged tile behave like an identity block
+        for (int i = nb + tid; i < PT; i += TS_THREADS) {
+            const int b = i >> 5;
+            Lp[ts_base(b) + (i - 32 * b) * ts_ld(b) + i] = 1.0;
         }
         __syncthreads();
-        if (it == 0 && nb < PT) {
-            // dead rows / columns of a ragged tile behave like an identity block
-            for (int i = nb + tid; i < PT; i += TS_THREADS) {
-                const int b = i >> 5;
-                Lp[ts_base(b) + (i - 32 * b) * ts_ld(b) + i] = 1.0;
-            }
-            __syncthreads();
-        }
-        // this lane's strip row (A-fragment row and C row); the ninth warp owns the extra rows' strip
-        double* xrow = warp < 8 ? Xs + (warp * 8 + gq) * TS_LD : Es + gq * TS_LD;
-        const bool active = warp < 8 || (it == 0 && nextra > 0);
-        for (int b = 0; b < (active ? 4 : 0); ++b) {
+    }
+    // the chunk that holds a diagonal entry of T also carries the entry right of it (zero in Tsub): fine.
+    const int gq = lane >> 2, kk = lane & 3;
+    // X = R L^-T for the 8-row strip whose lane row is xrow (A-fragment row and C row), in place
+    auto solve_strip = [&](double* xrow) {
+        for (int b = 0; b < 4; ++b) {
             const int cb = 32 * b, ldb = ts_ld(b);
             const double* Lb = Lp + ts_base(b) + gq * ldb + kk;  // + 8 j8 ldb + k
             double acc[4][2];
@@ -890,12 +887,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
                 acc[j8][0] = acc[j8][1] = 0.0;
             }
             __syncwarp();
-            // X_b = R T_bb^T : sum_k R[i][k] T_bb[j][k]  (T_bb lower: zeros above its diagonal are stored)
+            // X_b = R T_bb^T : sum_k R[i][k] T_bb[j][k]; T_bb is lower, so the 8-column tile j8 stops at k = 8 (j8 + 1)
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-                const double av = xrow[cb + k + kk];
+            for (int s = 0; s < 8; ++s) {
+                const double av = xrow[cb + 4 * s + kk];
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) dmma884(acc[j8][0], acc[j8][1], av, Lb[8 * j8 * ldb + cb + k]);
+                for (int j8 = 0; j8 < 4; ++j8)
+                    if (s < 2 * (j8 + 1)) dmma884(acc[j8][0], acc[j8][1], av, Lb[8 * j8 * ldb + cb + 4 * s]);
             }
             __syncwarp();
 #pragma unroll
@@ -905,9 +903,44 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
             }
             __syncwarp();
         }
+    };
+    if (half == 2) {
+        // seventeenth warp: the extra rows' strip, once
+        if (nextra) {
+            solve_strip(Es + gq * TS_LD);
+            __syncwarp();
+        }
         __syncthreads();
+        if (nextra && blockIdx.x == 0) {
+            // the solved extra rows themselves, in place
+            for (int e = lane; e < nextra * PT; e += 32) {
+                const int i = e >> 7, c = e & (PT - 1);
+                if (c < nb) E[(long long)i * a.lda + c] = Es[i * TS_LD + c];
+            }
+        }
+        return;
+    }
+    // the two halves (8 warps each, own buffer, own barrier) walk alternate row blocks independently: the
+    // load / store phases of one overlap the tensor-pipe phase of the other
+    bool first = true;
+    for (int it = half; it < nblocks || first; it += 2) {
+        const bool live = it < nblocks;
+        const int r0 = (blk0 + it) * TS_ROWS;
+        if (live) {
+            if (!first) {
+                stage_rows(blk0 + it);
+                cp_async_commit();
+                cp_async_wait<0>();
+                half_barrier(half);
+            }
+            solve_strip(Xs + (hw * 8 + gq) * TS_LD);
+        }
+        if (first) __syncthreads();  // the extra strip is solved (every warp passes here exactly once)
+        else half_barrier(half);
+        first = false;
+        if (!live) break;
         // write out: panel buffer + A in place (rows of this block), then the mirrored upper tiles
-        for (int e = tid; e < TS_ROWS * (PT / 2); e += TS_THREADS) {
+        for (int e = htid; e < TS_ROWS * (PT / 2); e += TS_HALF_THREADS) {
             const int r = e >> 6, c = (e & 63) * 2;
             if (r0 + r >= a.M || c >= nb) continue;
             const double v0 = Xs[r * TS_LD + c], v1 = Xs[r * TS_LD + c + 1];
@@ -924,46 +957,37 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
         }
         if (a.Aup && r0 < a.mirror_rows) {
             double* __restrict__ Aup = a.Aup + zb * a.strideA;
-            for (int e = tid; e < PT * TS_ROWS; e += TS_THREADS) {
+            for (int e = htid; e < PT * TS_ROWS; e += TS_HALF_THREADS) {
                 const int j = e >> 6, r = e & 63;  // consecutive threads -> consecutive rows r: contiguous in Aup
                 if (j < nb && r0 + r < a.mirror_rows) Aup[(long long)j * a.lda + r0 + r] = Xs[r * TS_LD + j];
             }
         }
-        if (nextra) {
+        if (nextra && r0 + hw * 8 < a.M) {
             // extra rows: their part right of the tile, columns of this block:  E[i][nb + r0 + r] -= X_E[i] . X[r]
             // one 8x8 output tile per warp (rows = extra rows, columns = the warp's own strip), K = 128 on DMMA
-            if (warp < 8 && r0 + warp * 8 < a.M) {
-                const double* er = Es + gq * TS_LD + kk;
-                const double* xr = Xs + (warp * 8 + gq) * TS_LD + kk;
-                double c[4][2];
+            const double* er = Es + gq * TS_LD + kk;
+            const double* xr = Xs + (hw * 8 + gq) * TS_LD + kk;
+            double c[4][2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = 0.0;
+            for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = 0.0;
 #pragma unroll
-                for (int k0 = 0; k0 < PT; k0 += 32) {
-                    double av[8], bv[8];
+            for (int k0 = 0; k0 < PT; k0 += 32) {
+                double av[8], bv[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { av[q] = er[k0 + 4 * q]; bv[q] = xr[k0 + 4 * q]; }
+                for (int q = 0; q < 8; ++q) { av[q] = er[k0 + 4 * q]; bv[q] = xr[k0 + 4 * q]; }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) dmma884(c[q & 3][0], c[q & 3][1], av[q], bv[q]);
-                }
-                const double s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
-                const double s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
-                const int r = warp * 8 + 2 * kk;
-                if (gq < nextra) {
-                    double* ep = E + (long long)gq * a.lda + nb + r0 + r;
-                    if (r0 + r < a.M) ep[0] -= s0;
-                    if (r0 + r + 1 < a.M) ep[1] -= s1;
-                }
+                for (int q = 0; q < 8; ++q) dmma884(c[q & 3][0], c[q & 3][1], av[q], bv[q]);
             }
-            if (it == 0 && blockIdx.x == 0) {
-                // the solved extra rows themselves, in place
-                for (int e = tid; e < nextra * PT; e += TS_THREADS) {
-                    const int i = e >> 7, c = e & (PT - 1);
-                    if (c < nb) E[(long long)i * a.lda + c] = Es[i * TS_LD + c];
-                }
+            const double s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+            const double s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+            const int r = hw * 8 + 2 * kk;
+            if (gq < nextra) {
+                double* ep = E + (long long)gq * a.lda + nb + r0 + r;
+                if (r0 + r < a.M) ep[0] -= s0;
+                if (r0 + r + 1 < a.M) ep[1] -= s1;
             }
         }
-        __syncthreads();  // the buffer is refilled by the prefetch of the next iteration
+        half_barrier(half);  // the buffer is refilled by the next iteration of this half
     }
 }
 
