@@ -88,6 +88,51 @@ __device__ __forceinline__ void smem_mma(int M8, int N8, int wid, int nw, FA a, 
     }
 }
 
+// Rank-32 update of lower 8x8 tiles:  C[i][j] -= sum_{k<32} P[i][k] P[j][k]  for the tile rows i8 in
+// [i8_lo, i8_hi) and j8 in [0, i8].  prow(r) / crow(r) return the address of row r of the 32-column panel / of
+// the target (column 0 = tile column 0).  The tiles are dealt to the warps in contiguous, equally long runs
+// (row-major), so a run mostly stays inside one tile row and keeps its A fragments; every tile is two
+// independent chains of four DMMAs.
+template <class RP, class RC>
+__device__ __forceinline__ void syrk32_rows(int i8_lo, int i8_hi, int wid, int nw, RP prow, RC crow) {
+    const int lane = threadIdx.x & 31;
+    const int gq = lane >> 2, kk = lane & 3;
+    const int total = (i8_hi * (i8_hi + 1) - i8_lo * (i8_lo + 1)) / 2;
+    const int run = (total + nw - 1) / nw;
+    int t = wid * run;
+    const int t_end = min(total, t + run);
+    if (t >= t_end) return;
+    int i8 = i8_lo, j8 = t;
+    while (j8 > i8) { j8 -= i8 + 1; ++i8; }
+    int loaded = -1;
+    double av[8];
+    for (; t < t_end; ++t) {
+        const int i = i8 * 8 + gq;
+        if (loaded != i8) {
+            const double* pa = prow(i) + kk;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) av[s] = pa[4 * s];
+            loaded = i8;
+        }
+        const double* pb = prow(j8 * 8 + gq) + kk;
+        double bv[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) bv[s] = pb[4 * s];
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < 8; s += 2) {
+            dmma884(c0, c1, av[s], bv[s]);
+            dmma884(d0, d1, av[s + 1], bv[s + 1]);
+        }
+        double* cr = crow(i);
+        const int j = j8 * 8 + 2 * kk;
+        // diagonal 8x8 tiles: touch the lower part only (the upper part is reserved for T^T)
+        if (j <= i) cr[j] -= c0 + d0;
+        if (j + 1 <= i) cr[j + 1] -= c1 + d1;
+        if (++j8 > i8) { j8 = 0; ++i8; }
+    }
+}
+
 // Factor one 128x128 diagonal tile (lower) and invert the factor.  One CTA per tile.
 //
 // The tile lives in shared memory for the whole kernel:  S lower = L,  S strict upper = T^T
@@ -145,7 +190,19 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
     for (int jb = 0; jb < (a.mode == POTF2_INVERT ? 0 : 4); ++jb) {
         const int c0 = jb * 32;
         POTF2_STAMP(2 + 3 * jb);
-        if (warp == 0) {
+        if (warp != 0) {
+            // look-ahead: while warp 0 factors this diagonal block, the other warps finish the previous panel's
+            // trailing update (everything but this diagonal block, which was updated first)
+            if (jb > 0) {
+                const double* P = S + c0 * PLD + c0 - 32;
+                double* C = S + c0 * PLD + c0;
+                // (warps of warp 0's scheduler partition stay out: the pivot chain's DFMAs would queue behind
+                // their DMMAs in the shared FP64 pipe)
+                if (warp & 3)
+                    syrk32_rows(4, (PT - c0) / 8, warp - 1 - (warp >> 2), nwarps - nwarps / 4,
+                                [&](int r) { return P + r * PLD; }, [&](int r) { return C + r * PLD; });
+            }
+        } else {
             double* D = S + c0 * PLD + c0;
             for (int sb = 0; sb < 4; ++sb) {
                 const int o = sb * 8;
@@ -258,17 +315,11 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
             }
             __syncthreads();
             POTF2_STAMP(4 + 3 * jb);
-            // trailing update of the lower 8x8 tiles: S[rb.., rb..] -= P P^T, P = S[rb.., c0..c0+32)
+            // trailing update, first part: the next diagonal block only (lower 8x8 tiles of S[rb..rb+32, rb..rb+32)
+            // -= P P^T, P = S[rb.., c0..c0+32)); the rest follows under the next block's pivot chain
             const double* P = S + rb * PLD + c0;
             double* C = S + rb * PLD + rb;
-            smem_mma<32>(
-                mrows / 8, mrows / 8, warp, nwarps, [&](int i, int k) { return P[i * PLD + k]; },
-                [&](int j, int k) { return P[j * PLD + k]; }, [&](int i8, int j8) { return j8 <= i8; },
-                [&](int i, int j, double c0v, double c1v) {
-                    // diagonal 8x8 tiles: touch the lower part only (the upper part is reserved for T^T)
-                    if (j <= i) C[i * PLD + j] -= c0v;
-                    if (j + 1 <= i) C[i * PLD + j + 1] -= c1v;
-                });
+            syrk32_rows(0, 4, warp, nwarps, [&](int r) { return P + r * PLD; }, [&](int r) { return C + r * PLD; });
             __syncthreads();
         }
     }
@@ -487,7 +538,17 @@ __global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2
     for (int jb = 0; jb < 4; ++jb) {
         const int c0 = jb * 32, ldd = ts_ld(jb);
         double* D = S + pk(c0, c0);  // diagonal block: rows share the leading dimension ldd
-        if (warp == 0) {
+        if (warp != 0) {
+            // look-ahead: the other warps finish the previous panel's trailing update (everything but this
+            // diagonal block, updated first) while warp 0 walks the pivot chain
+            if (jb > 0) {
+                // (warp 4 shares warp 0's scheduler partition and FP64 pipe: it stays out)
+                if (warp & 3)
+                    syrk32_rows(4, (PT - c0) / 8, warp - 1 - (warp >> 2), nwarps - nwarps / 4,
+                                [&](int r) { return S + pk(c0 + r, c0 - 32); },
+                                [&](int r) { return S + pk(c0 + r, c0); });
+            }
+        } else {
             for (int sb = 0; sb < 4; ++sb) {
                 const int o = sb * 8;
                 if (lane == 0) {
@@ -595,16 +656,9 @@ __global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2
                 for (int k = 0; k < 32; ++k) prow[k] = x[k];
             }
             __syncthreads();
-            // trailing update of the lower 8x8 tiles: S[rb.., rb..] -= P P^T, P = S[rb.., c0..c0+32)
-            smem_mma<32>(
-                mrows / 8, mrows / 8, warp, nwarps, [&](int i, int k) { return S[pk(rb + i, c0 + k)]; },
-                [&](int j, int k) { return S[pk(rb + j, c0 + k)]; }, [&](int i8, int j8) { return j8 <= i8; },
-                [&](int i, int j, double c0v, double c1v) {
-                    // diagonal 8x8 tiles: touch the lower part only (the upper part is reserved for T^T)
-                    double* cp = S + pk(rb + i, rb + j);
-                    if (j <= i) cp[0] -= c0v;
-                    if (j + 1 <= i) cp[1] -= c1v;
-                });
+            // trailing update, first part: the next diagonal block only; the rest follows under the next chain
+            syrk32_rows(0, 4, warp, nwarps, [&](int r) { return S + pk(rb + r, c0); },
+                        [&](int r) { return S + pk(rb + r, rb); });
             __syncthreads();
         }
     }
