@@ -42,9 +42,9 @@ METRIC = "REML logL+grad evals/s (n=8192,d=8,fp64)"
 FP64_NOMINAL_TFLOPS = 40.0  # HGX B200 datasheet; MEASURED_PEAKS.json carries no fp64 entry
 # DRAM bytes of all DMMA launches (gemm_nt_kernel + trsm_tile_kernel) of one evaluation: dram__bytes_read.sum +
 # dram__bytes_write.sum summed over the 201 launches, ncu capture committed as
-# profiles/r01_gemm_dram_one_eval.csv (10.12 GB read + 1.29 GB written: 64x64 tiles re-read operands from L2/HBM
+# profiles/r01_gemm_dram_one_eval.csv (10.23 GB read + 1.29 GB written: 64x64 tiles re-read operands from L2/HBM
 # more often than 128x128 tiles did -- 5.6 GB -- and still sit at ~0.5 TB/s, far below the HBM roofline)
-GEMM_DRAM_BYTES_PER_STEP = 10.117e9 + 1.288e9
+GEMM_DRAM_BYTES_PER_STEP = 10.227e9 + 1.286e9
 
 
 def headline_inputs(n=N_OBS, d=DIM, seed=SEED):

@@ -397,6 +397,25 @@ def test_batched_matches_scalar_path_n512(gp):
     assert relerr(vals[3], ref) <= TOL_LIK
 
 
+@pytest.mark.parametrize("kind,mean,d", [("ml", "zero", 3), ("reml", "linear", 4), ("reml", "linear", 8)])
+def test_batched_extra_rows_variants(gp, kind, mean, d):
+    """The whitening rows ride through the batched panel solves as an extra strip when there are at most 8 of
+    them (zero mean: 1 row, linear d=4: 6 rows) and as ordinary panel rows otherwise (linear d=8: 10 rows):
+    both must reproduce the scalar path."""
+    n = 300
+    x, z, _ = cases.data(n, d, 31)
+    th0 = cases.theta(d, 31)
+    TH = th0 + np.random.default_rng(32).uniform(-0.7, 0.7, size=(7, d + 1))
+    m = _model(gp, mean, 2, False, th0)
+    vals = gp.batched.BatchedCriterion(m, x, z, 2, kind=kind)(TH)
+    for i in range(7):
+        if kind == "ml":
+            v = m.negative_log_likelihood_zero_mean(TH[i], x, z).item()
+        else:
+            v = m.negative_log_restricted_likelihood(TH[i], x, z).item()
+        assert relerr(vals[i], v) <= 1e-11, (i, vals[i], v)
+
+
 def test_edge_shapes_and_inputs(gp):
     """Edge cases the reference's call conventions allow: a (n,1) column for zi, NumPy covparam, a wide
     linear basis (q = d + 1 = 11), d = 32, n = 1, empty prediction sets."""
