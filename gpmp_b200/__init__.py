@@ -10,7 +10,7 @@ All arithmetic runs in libgpmp_b200.so (hand-written sm_100a kernels behind the 
 include/gpmp_b200.h).  There is no CPU fallback: importing works anywhere, calling needs a CUDA device
 and the built library.
 """
-from . import _abi, batched, core, dist, kernel, num, ops, selection  # noqa: F401
+from . import _abi, batched, core, dist, fisher, kernel, num, ops, selection  # noqa: F401
 from .core import Model  # noqa: F401
 
 __version__ = "0.1.0"

@@ -168,6 +168,17 @@ class Model:
             state.kernel = None
         return state, out
 
+    # ------------------------------------------------------------------ Fisher information
+    def fisher_information(self, xi, covparam=None, epsilon=1e-3):
+        """0.5 tr(K^-1 dK_i K^-1 dK_j), dK by 5-point differences (core/model.py:509-538, core/fisher.py:18-78)."""
+        from . import fisher
+        return fisher.fisher_information(self, xi, covparam=covparam, epsilon=epsilon)
+
+    def fisher_information_cpd(self, xi, covparam=None, epsilon=1e-3):
+        """Contrast-space form for a linear-predictor mean (core/model.py:540-575, core/fisher.py:81-155)."""
+        from . import fisher
+        return fisher.fisher_information_cpd(self, xi, covparam=covparam, epsilon=epsilon)
+
     # ------------------------------------------------------------------ leave-one-out
     def loo(self, xi, zi, convert_in=True, convert_out=False):
         """Leave-one-out predictions, variances and errors by virtual cross-validation

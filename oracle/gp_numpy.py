@@ -406,6 +406,44 @@ def conditional_sample_paths_parameterized_mean(model, ztsim, xi, xi_ind, zi, xt
 # --------------------------------------------------------------------------
 # L4 boundary: particle-batched criterion (mcmc/param_posterior.py:739-759)
 # --------------------------------------------------------------------------
+# --------------------------------------------------------------------------
+# Fisher information (core/fisher.py:18-155, num/shared.py:44-55)
+# --------------------------------------------------------------------------
+def _covariance_derivatives(model, xi, theta, epsilon):
+    """dK/dtheta_i by the reference's 5-point central difference (num/shared.py:44-55)."""
+    out = []
+    for i in range(theta.shape[0]):
+        def f(v):
+            t = theta.copy()
+            t[i] = v
+            return model.covariance(xi, xi, t)
+
+        h = epsilon
+        out.append((-f(theta[i] + 2 * h) + 8 * f(theta[i] + h) - 8 * f(theta[i] - h) + f(theta[i] - 2 * h)) / (12.0 * h))
+    return out
+
+
+def fisher_information(model, xi, covparam=None, epsilon=1e-3):
+    """I_ij = 0.5 tr(K^-1 dK_i K^-1 dK_j)  (core/fisher.py:18-78)."""
+    theta = np.asarray(model.covparam if covparam is None else covparam, dtype=np.float64)
+    Kinv = np.linalg.inv(model.covariance(xi, xi, theta))
+    B = [Kinv @ dK for dK in _covariance_derivatives(model, xi, theta, epsilon)]
+    p = theta.shape[0]
+    return np.array([[0.5 * np.trace(B[i] @ B[j]) for j in range(p)] for i in range(p)])
+
+
+def fisher_information_cpd(model, xi, covparam=None, epsilon=1e-3):
+    """Contrast-space form G = W'KW for a linear-predictor mean (core/fisher.py:81-155)."""
+    if model.meantype != "linear_predictor":
+        return fisher_information(model, xi, covparam, epsilon)
+    theta = np.asarray(model.covparam if covparam is None else covparam, dtype=np.float64)
+    W = contrast_matrix(np.asarray(model.mean(xi, model.meanparam)))
+    G = W.T @ (model.covariance(xi, xi, theta) @ W)
+    B = [np.linalg.solve(G, W.T @ (dK @ W)) for dK in _covariance_derivatives(model, xi, theta, epsilon)]
+    p = theta.shape[0]
+    return np.array([[0.5 * np.trace(B[i] @ B[j]) for j in range(p)] for i in range(p)])
+
+
 def logpdf_temp(criterion, x, temperature, lower_b=None, upper_b=None):
     """Serial per-particle loop of param_posterior.py:742-759: -J(theta_i)/T, -inf outside the box."""
     x = np.asarray(x, dtype=np.float64)

@@ -416,6 +416,29 @@ def test_batched_extra_rows_variants(gp, kind, mean, d):
         assert relerr(vals[i], v) <= 1e-11, (i, vals[i], v)
 
 
+def _fisher_cases():
+    from oracle.make_golden_fisher import FISHER_CASES
+    return FISHER_CASES
+
+
+@pytest.mark.parametrize("case", [c[0] for c in _fisher_cases()])
+def test_fisher_information(gp, case):
+    """Model.fisher_information / _cpd against the reference's core/fisher.py (golden vectors).  Both sides
+    difference K at steps of 1e-3, so entry-level rounding of K (1e-13) is amplified by 1e3 cond(K): 1e-6."""
+    import os
+    name, n, d, p, kind, noise, seed = next(c for c in _fisher_cases() if c[0] == case)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_fisher.npz"))
+    x, th = g[name + "/x"], g[name + "/theta"]
+    m = _model(gp, kind, p, noise, th)
+    for form, fn in (("spd", m.fisher_information), ("cpd", m.fisher_information_cpd)):
+        ref = g[name + "/" + form]
+        got = fn(x, th).cpu().numpy()
+        assert got.shape == ref.shape and np.allclose(got, got.T)
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) <= 1e-6, (form, got, ref)
+    # default covparam = model.covparam
+    assert np.array_equal(m.fisher_information(x).cpu().numpy(), m.fisher_information(x, th).cpu().numpy())
+
+
 def test_edge_shapes_and_inputs(gp):
     """Edge cases the reference's call conventions allow: a (n,1) column for zi, NumPy covparam, a wide
     linear basis (q = d + 1 = 11), d = 32, n = 1, empty prediction sets."""
