@@ -86,6 +86,9 @@ SIGNATURES = {
     "gpmp_lik_trsm_rows": (_i, [_i, _i, _vp, _sz, _vp, _i, _ll, _i, _vp, _vp]),
     "gpmp_criterion_batched_bytes": (_sz, [_i, _i, _i]),
     "gpmp_criterion_batched": (_i, [_specp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp]),
+    "gpmp_criterion_batched_grad_bytes": (_sz, [_i, _i, _i, _i]),
+    "gpmp_criterion_batched_grad": (_i, [_specp, _vp, _i, _vp, _ll, _i, _vp, _ll, _vp, _i, _vp, _sz, _vp, _vp, _vp,
+                                         _vp]),
 }
 
 _ERR = {-1: "bad argument", -2: "dimension or regularity out of range", -3: "workspace too small",

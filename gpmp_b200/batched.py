@@ -36,6 +36,7 @@ class BatchedCriterion:
         self.group = group
         self.max_bytes = max_bytes
         self._work = None  # device workspace, allocated at the first sweep and reused
+        self._gwork, self._grows = None, 0
 
     def values_device(self, thetas):
         """thetas: (N, 1+noise+d) array-like -> (values, info) device tensors for the local shard."""
@@ -46,6 +47,29 @@ class BatchedCriterion:
             self._work = ops.criterion_batched_workspace(n, q, th.shape[0], self.max_bytes)
             self._rows = th.shape[0]
         return ops.criterion_batched(th, self.x, self.z, self.P, self.p, self.noise, self.max_bytes, self._work)
+
+    def value_and_grad(self, thetas, convert_out=True):
+        """Criterion values and gradients at every row of thetas in one launch sequence: the batched form of
+        `gnp.value_and_grad(criterion)` per particle (mcmc/svgd.py:310-313, torch_backend.py:516-533).
+        Returns (values[N], grads[N, 1+noise+d]); rows are block-partitioned over ranks like the values."""
+        th = np.asarray(thetas.detach().cpu() if torch.is_tensor(thetas) else thetas, dtype=np.float64)
+        if th.ndim == 1:
+            th = th.reshape(1, -1)
+        N = th.shape[0]
+        lo, hi = gdist.shard_bounds(N, self.group)
+        thd = ops.to_device(th[lo:hi])
+        n, d = self.x.shape
+        q = 0 if self.P is None else self.P.shape[1]
+        if self._gwork is None or self._grows < thd.shape[0]:
+            self._gwork = ops.criterion_batched_grad_workspace(n, q, d, thd.shape[0], self.max_bytes)
+            self._grows = thd.shape[0]
+        vals, grads, _ = ops.criterion_batched_grad(thd, self.x, self.z, self.P, self.p, self.noise,
+                                                    self.max_bytes, self._gwork)
+        vals = gdist.all_gather_rows(vals, N, self.group)
+        grads = gdist.all_gather_rows(grads, N, self.group)
+        if convert_out:
+            return vals.cpu().numpy(), grads.cpu().numpy()
+        return vals, grads
 
     def __call__(self, thetas, convert_out=True):
         th = np.asarray(thetas.detach().cpu() if torch.is_tensor(thetas) else thetas, dtype=np.float64)
@@ -68,3 +92,104 @@ class BatchedCriterion:
             inside = np.all((th >= np.asarray(lower)) & (th <= np.asarray(upper)), axis=1)
             out = np.where(inside, out, -np.inf)
         return out
+
+
+class MiniBatchCriterion:
+    """Selection criterion summed over mini-batches, all equal-size batches in ONE batched launch sequence.
+
+    Mirrors `BatchDifferentiableSelectionCriterion` (gpmp/num/torch_backend.py:607-718): value = sum over
+    batches of criterion(param, x_b, z_b) * len(batch), divided by the number of points for reduction="mean";
+    `evaluate_pre_grad` caches the gradient that `gradient` returns.  `loader` is any iterable of (x_b, z_b)
+    pairs (a torch DataLoader or a list); batches of the most common size are stacked and go through
+    gpmp_criterion_batched_grad with one point set per entry, the remaining (ragged) batches through the scalar
+    fused path.  The per-batch criterion is the model's REML (kind="reml", constant or zero mean shared by all
+    batches) or zero-mean ML (kind="ml"); covariance = Matern-p with the package's parameter layout.
+    """
+
+    def __init__(self, model, loader, p, kind="reml", noise=False, reduction="mean", batches_per_eval=0):
+        if reduction not in ("mean", "sum"):
+            raise ValueError("reduction must be 'mean' or 'sum'")
+        if batches_per_eval < 0:
+            raise ValueError("batches_per_eval must be >= 0")
+        if kind not in ("reml", "ml"):
+            raise ValueError("kind must be 'reml' or 'ml'")
+        if len(loader) == 0:
+            raise ValueError("DataLoader is empty.")
+        self.model, self.loader, self.p, self.kind, self.noise = model, loader, int(p), kind, bool(noise)
+        self.reduction, self.bpe = reduction, int(batches_per_eval)
+        self._batch_iter = iter(loader) if self.bpe > 0 else None
+        self._gradient = None
+        self._work, self._wkey = None, None
+
+    def _batches(self):
+        if self.bpe == 0:
+            yield from self.loader
+        else:
+            for _ in range(self.bpe):
+                try:
+                    yield next(self._batch_iter)
+                except StopIteration:
+                    self._batch_iter = iter(self.loader)
+                    yield next(self._batch_iter)
+
+    def _basis(self, xb):
+        if self.kind != "reml":
+            return None
+        P = ops.to_device(self.model.mean(xb, self.model.meanparam))
+        return (P.reshape(-1, 1) if P.dim() == 1 else P).contiguous()
+
+    def _evaluate(self, param, want_grad):
+        theta = ops.to_device(param).reshape(-1).detach()
+        batches = [(ops.to_device(xb), ops.to_device(zb).reshape(-1)) for xb, zb in self._batches()]
+        sizes = [b[0].shape[0] for b in batches]
+        npts = sum(sizes)
+        if npts == 0:
+            raise ValueError("Loader is empty.")
+        common = max(set(sizes), key=sizes.count)
+        same = [b for b in batches if b[0].shape[0] == common]
+        rest = [b for b in batches if b[0].shape[0] != common]
+        total = torch.zeros((), dtype=torch.float64, device=theta.device)
+        grad = torch.zeros_like(theta)
+        if same:
+            X = torch.stack([b[0] for b in same]).contiguous()
+            Z = torch.stack([b[1] for b in same]).contiguous()
+            P = self._basis(same[0][0])
+            if P is not None and P.shape[1] > 0 and not all(torch.equal(self._basis(b[0]), P) for b in same[1:]):
+                # basis depends on the points (e.g. linear mean): no shared P, take the scalar path for all
+                rest, same = batches, []
+            else:
+                B, n, d = X.shape
+                q = 0 if P is None else P.shape[1]
+                key = (B, n, d, q)
+                if self._wkey != key:
+                    self._work, self._wkey = ops.criterion_batched_grad_workspace(n, q, d, B), key
+                TH = theta.reshape(1, -1).repeat(B, 1)
+                vals, grads, info = ops.criterion_batched_grad(TH, X, Z, P, self.p, self.noise, work=self._work)
+                total = total + vals.sum() * common
+                grad = grad + grads.sum(dim=0) * common
+        for xb, zb in rest:
+            tp = theta.clone().requires_grad_(want_grad)
+            v = ops.fused_likelihood(tp, zb.contiguous(), xb.contiguous(), self._basis(xb), self.p, self.noise)
+            if want_grad:
+                (g,) = torch.autograd.grad(v, tp)
+                grad = grad + g.to(grad.device) * xb.shape[0]
+            total = total + v.detach().to(total.device) * xb.shape[0]
+        if self.reduction == "mean":
+            total, grad = total / npts, grad / npts
+        return float(total), grad
+
+    def evaluate(self, param):
+        return self._evaluate(param, False)[0]
+
+    def evaluate_no_grad(self, param):
+        return self._evaluate(param, False)[0]
+
+    def evaluate_pre_grad(self, param):
+        value, grad = self._evaluate(param, True)
+        self._gradient = grad.detach().cpu()
+        return value
+
+    def gradient(self, _param):
+        if self._gradient is None:
+            raise RuntimeError("Call `evaluate` first.")
+        return self._gradient

@@ -696,4 +696,114 @@ int gpmp_criterion_batched(const gpmp_cov_spec* spec, const double* theta_dev, i
     return GPMP_OK;
 }
 
+
+// ---- batched criterion with gradients (SVGD particles, mini-batches) -----------------------------------------
+// Entry b: theta_b, points x + b x_stride, observations z + b z_stride (strides in elements, 0 = shared), shared
+// mean basis P.  Same pipeline as gpmp_lik_value + gpmp_lik_grad with a batch dimension: K build, factorisation
+// with the tile inverses kept, whitening, T by block doubling, K^-1 = T^T T, U = [Q~; r] T, contraction against
+// the regenerated dK tiles.  Workspace per entry: the matrix, three n x n matrices (Tlo, Tup, K^-1) and panels.
+struct BatchGradWs {
+    BatchWs v;
+    size_t per_full, per_U, per_partial, per_entry;
+};
+static BatchGradWs batch_grad_ws(int n, int q, int d) {
+    BatchGradWs g;
+    g.v = batch_ws(n, q);
+    g.per_full = align_up((size_t)n * g.v.lda * 8, 256);
+    g.per_U = align_up((size_t)g.v.r * g.v.lda * 8, 256);
+    g.per_partial = align_up(contract_workspace_bytes(n, n, d), 256);
+    g.per_entry = g.v.per_A + 2 * g.v.per_T + g.v.per_W + g.v.per_mdev + 3 * g.per_full + g.per_U + g.per_partial;
+    return g;
+}
+
+size_t gpmp_criterion_batched_grad_bytes(int n, int q, int d, int nbatch) {
+    if (n <= 0 || q < 0 || d <= 0 || nbatch <= 0) return 0;
+    BatchGradWs g = batch_grad_ws(n, q, d);
+    return g.v.shared + (size_t)nbatch * g.per_entry;
+}
+
+int gpmp_criterion_batched_grad(const gpmp_cov_spec* spec, const double* theta_dev, int N, const double* x_dev,
+                                long long x_stride, int n, const double* z_dev, long long z_stride,
+                                const double* P_dev, int q, void* work_dev, size_t work_bytes, double* values_dev,
+                                double* grads_dev, int* info_dev, void* stream) {
+    if (!spec || !theta_dev || !x_dev || !z_dev || !work_dev || !values_dev || !grads_dev || !info_dev)
+        return GPMP_ERR_ARG;
+    if (n <= 0 || N < 0 || q < 0 || q > GPMP_MAX_Q || (q > 0 && !P_dev) || x_stride < 0 || z_stride < 0)
+        return GPMP_ERR_ARG;
+    if (N == 0) return GPMP_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    BatchGradWs gw = batch_grad_ws(n, q, spec->d);
+    const BatchWs& w = gw.v;
+    if (work_bytes < w.shared + gw.per_entry) return GPMP_ERR_WORKSPACE;
+    long long cap = (long long)((work_bytes - w.shared) / gw.per_entry);
+    if (cap > 32768) cap = 32768;
+    if (cap > N) cap = N;
+    char* base = static_cast<char*>(work_dev);
+    size_t rowsb = align_up((size_t)(q > 0 ? q : 1) * w.lda * 8, 256);
+    double* p0rows = (double*)base;
+    double* p0work = (double*)(base + rowsb);
+    double* ldr0 = (double*)(base + 2 * rowsb);
+    char* pbase = base + w.shared;
+    size_t off = 0;
+    double* A = (double*)(pbase + off); off += (size_t)cap * w.per_A;
+    double* Tlo_c = (double*)(pbase + off); off += (size_t)cap * w.per_T;
+    double* Tup_c = (double*)(pbase + off); off += (size_t)cap * w.per_T;
+    double* W = (double*)(pbase + off); off += (size_t)cap * w.per_W;
+    MaternDev* mdev = (MaternDev*)(pbase + off); off += (size_t)cap * w.per_mdev;
+    double* Tlo = (double*)(pbase + off); off += (size_t)cap * gw.per_full;
+    double* Tup = (double*)(pbase + off); off += (size_t)cap * gw.per_full;
+    double* Kinv = (double*)(pbase + off); off += (size_t)cap * gw.per_full;
+    double* U = (double*)(pbase + off); off += (size_t)cap * gw.per_U;
+    double* partial = (double*)(pbase + off);
+    const long long sA = (long long)(w.per_A / 8), sT = (long long)(w.per_T / 8), sW = (long long)(w.per_W / 8);
+    const long long sF = (long long)(gw.per_full / 8), sU = (long long)(gw.per_U / 8);
+    int rc;
+    if (cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)N, s) != cudaSuccess) return GPMP_ERR_CUDA;
+    const int w_theta = 1 + spec->noise + spec->d;
+    for (long long c0 = 0; c0 < N; c0 += cap) {
+        const int nb = (int)((N - c0) < cap ? (N - c0) : cap);
+        const double* xb = x_dev + c0 * x_stride;
+        rc = launch_prep_theta(spec, theta_dev + c0 * w_theta, nb, 1, mdev, s);
+        if (rc) return rc;
+        rc = launch_matern_cov(spec, mdev, nb, sA, xb, n, nullptr, n, A, w.lda, COV_SYM_LOWER, 0, s, x_stride);
+        if (rc) return rc;
+        LoadRowsArgs lr;
+        lr.P = P_dev; lr.z = z_dev + c0 * z_stride; lr.strideZ = z_stride; lr.n = n; lr.q = q;
+        lr.rows = A + (long long)n * w.lda; lr.ld = w.lda; lr.stride = sA;
+        lr.p0rows = (q > 0 && c0 == 0) ? p0rows : nullptr; lr.ld0 = w.lda;
+        rc = launch_load_rows(lr, nb, s);
+        if (rc) return rc;
+        // factorisation with the 128-wide tile inverses and the NB-wide block inverses (no Tsub: full path)
+        rc = potrf_core(A, w.lda, sA, n, w.nrows, w.NB, Tlo_c, Tup_c, sT, W, sW, info_dev + c0, 1, nb, s, nullptr, 0);
+        if (rc) return rc;
+        FinalizeArgs f;
+        f.rows = lr.rows; f.ld = w.lda; f.strideRows = sA;
+        f.p0rows = p0rows; f.ld0 = w.lda; f.p0work = p0work; f.strideP0 = 0;
+        f.Ldiag = A; f.ldl = w.lda; f.strideL = sA;
+        f.n = n; f.q = q;
+        f.Rt = nullptr; f.strideRt = 0;
+        f.info = info_dev + c0; f.strideInfo = 1;
+        f.out = values_dev + c0; f.strideOut = 1;
+        f.ldr0_in = q > 0 ? ldr0 : nullptr;
+        if (c0 == 0 && q > 0) {
+            rc = launch_logdet_r0(p0rows, p0work, w.lda, n, q, ldr0, s);
+            if (rc) return rc;
+        }
+        rc = launch_finalize(f, nb, s);
+        if (rc) return rc;
+        rc = potri_core(A, n, w.lda, w.NB, Tlo_c, Tup_c, Tlo, Tup, Kinv, w.lda, s, nb, sA, sT, sF);
+        if (rc) return rc;
+        URowsArgs u;
+        u.R = lr.rows; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;
+        u.n = n; u.j0 = 0; u.j1 = 0; u.batch = nb; u.strideR = sA; u.strideT = sF; u.strideU = sU;
+        rc = launch_urows(u, s);
+        if (rc) return rc;
+        ContractBatch cb{nb, mdev, sF, sU, x_stride};
+        rc = launch_contract(spec, xb, n, nullptr, n, Kinv, w.lda, U, w.lda, w.r, 1, 0, 0.5,
+                             grads_dev + c0 * w_theta, partial, (size_t)cap * gw.per_partial, s, 0, -1, &cb);
+        if (rc) return rc;
+    }
+    return GPMP_OK;
+}
+
 }  // extern "C"

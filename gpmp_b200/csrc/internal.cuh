@@ -21,12 +21,15 @@ int launch_prep_theta(const gpmp_cov_spec* spec, const double* theta_dev, int N,
                       cudaStream_t stream);
 int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batch, long long strideK,
                       const double* x, int n, const double* y, int mcols, double* K, long long ldk, int mode,
-                      int dist_only, cudaStream_t stream);
+                      int dist_only, cudaStream_t stream, long long strideX = 0);
 size_t contract_workspace_bytes(int n, int mcols, int d);
+// batched contraction: entry b uses mdev[b], G + b strideG, Ut + b strideU, x + b strideX (elements) and writes
+// grad + b (1 + noise + d); partial must hold batch x tiles x (2 + d) doubles
+struct ContractBatch { int batch; const MaternDev* mdev; long long strideG, strideU, strideX; };
 int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const double* y, int mcols, const double* G,
                     long long ldg, const double* Ut, long long ldu, int r, int sym, int dist_only, double half,
                     double* grad, void* partial, size_t partial_bytes, cudaStream_t stream, int tile_row0 = 0,
-                    int tile_row1 = -1);
+                    int tile_row1 = -1, const ContractBatch* cb = nullptr);
 int launch_pairwise(const gpmp_cov_spec* spec, const double* x, const double* y, int n, double* out, int dist_only,
                     cudaStream_t stream);
 int launch_maternp_elementwise(int p, const double* h, double* k, double* dk, long long count, cudaStream_t stream);
@@ -37,7 +40,8 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
                cudaStream_t stream, double* Tsub = nullptr, long long strideTsub = 0);
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
-               double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream);
+               double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream, int batch = 1,
+               long long strideL = 0, long long strideTc = 0, long long strideT = 0);
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,
                    double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream,
                    int first_block = 0);
@@ -57,6 +61,7 @@ struct LoadRowsArgs {
     const double* P; const double* z; int n, q;
     double* rows; long long ld; long long stride;  // destination rows (q+1) x ld
     double* p0rows; long long ld0;                  // optional second copy of the P rows (batch 0 only)
+    long long strideZ = 0;                          // batch stride of z (elements; 0 = shared observations)
 };
 
 struct FinalizeArgs {
@@ -77,6 +82,7 @@ struct URowsArgs {
     double* U; long long ldu;
     int n;
     int j0, j1;  // columns of U to compute: [j0, j1)  (j1 <= 0: all)
+    int batch = 1; long long strideR = 0, strideT = 0, strideU = 0;  // batched form (blockIdx.y = entry)
 };
 
 struct DenseGradArgs {

@@ -24,7 +24,7 @@ __global__ void load_rows_kernel(const LoadRowsArgs a) {
         rows[(long long)j * a.ld + i] = v;
         if (a.p0rows && blockIdx.z == 0) a.p0rows[(long long)j * a.ld0 + i] = v;
     }
-    rows[(long long)a.q * a.ld + i] = a.z[i];
+    rows[(long long)a.q * a.ld + i] = a.z[(long long)blockIdx.z * a.strideZ + i];
 }
 int launch_load_rows(const LoadRowsArgs& a, int batch, cudaStream_t stream) {
     LaunchScope scope(KC_SMALL, 0.0, stream);
@@ -210,7 +210,10 @@ __global__ void __launch_bounds__(UR_WARPS * 32) urows_kernel(const URowsArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = a.j0 + blockIdx.x * UR_WARPS + warp;
     if (j >= a.j1) return;
-    const double* __restrict__ t = a.Tup + (long long)j * a.ldt;
+    const long long zb = blockIdx.y;
+    const double* __restrict__ R = a.R + zb * a.strideR;
+    double* __restrict__ U = a.U + zb * a.strideU;
+    const double* __restrict__ t = a.Tup + zb * a.strideT + (long long)j * a.ldt;
     for (int a0 = 0; a0 < a.r; a0 += 4) {
         const int cnt = min(4, a.r - a0);
         double s[4] = {0.0, 0.0, 0.0, 0.0};
@@ -218,13 +221,13 @@ __global__ void __launch_bounds__(UR_WARPS * 32) urows_kernel(const URowsArgs a)
             const double tv = t[k];
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                if (c < cnt) s[c] = fma(tv, a.R[(long long)(a0 + c) * a.ldr + k], s[c]);
+                if (c < cnt) s[c] = fma(tv, R[(long long)(a0 + c) * a.ldr + k], s[c]);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (c < cnt) {
                 const double v = warp_sum(s[c]);
-                if (lane == 0) a.U[(long long)(a0 + c) * a.ldu + j] = v;
+                if (lane == 0) U[(long long)(a0 + c) * a.ldu + j] = v;
             }
         }
     }
@@ -235,8 +238,9 @@ int launch_urows(const URowsArgs& a0, cudaStream_t stream) {
     if (a.j1 <= 0 || a.j1 > a.n) a.j1 = a.n;
     if (a.j0 < 0) a.j0 = 0;
     if (a.j0 >= a.j1) return GPMP_OK;
-    LaunchScope scope(KC_SMALL, 8.0 * a.n * (a.n + 1.0) / 2.0, stream);
-    urows_kernel<<<ceil_div(a.j1 - a.j0, UR_WARPS), UR_WARPS * 32, 0, stream>>>(a);
+    LaunchScope scope(KC_SMALL, 8.0 * a.n * (a.n + 1.0) / 2.0 * a.batch, stream);
+    dim3 grid(ceil_div(a.j1 - a.j0, UR_WARPS), a.batch > 0 ? a.batch : 1);
+    urows_kernel<<<grid, UR_WARPS * 32, 0, stream>>>(a);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
 }

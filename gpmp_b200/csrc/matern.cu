@@ -164,6 +164,7 @@ struct CovArgs {
     MaternDev m;
     const MaternDev* mdev;  // optional per-batch parameters (device array indexed by blockIdx.z)
     long long strideK;      // batch stride of K (elements)
+    long long strideX;      // batch stride of the point set (elements; 0 = every entry uses the same points)
     const double* x; const double* y;
     double* K; long long ldk;
     int n, mcols;
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a
     }
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int r0 = ti * CT, c0 = tj * CT;
-    stage_points(xs, a.x, r0, a.n, m, tid);
-    stage_points(ys, a.y, c0, a.mcols, m, tid);
+    stage_points(xs, a.x + (long long)blockIdx.z * a.strideX, r0, a.n, m, tid);
+    stage_points(ys, a.y + (long long)blockIdx.z * a.strideX, c0, a.mcols, m, tid);
     __syncthreads();
 
     double h2[4][4];
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a
 // p and d for the host-side checks); K advances by strideK per batch entry, x / y are shared.
 int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batch, long long strideK,
                       const double* x, int n, const double* y, int mcols, double* K, long long ldk, int mode,
-                      int dist_only, cudaStream_t stream) {
+                      int dist_only, cudaStream_t stream, long long strideX) {
     if (n <= 0 || mcols <= 0 || batch <= 0) return GPMP_OK;
     const bool same = (y == nullptr || y == x) ;
     if (mode != CM_RECT && !same) return GPMP_ERR_ARG;
@@ -315,6 +316,7 @@ int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batc
     if (rc) return rc;
     a.mdev = mdev;
     a.strideK = strideK;
+    a.strideX = strideX;
     a.x = x;
     a.y = same ? x : y;
     a.K = K;
@@ -401,6 +403,8 @@ struct ContractArgs {
     int dist_only;    // vjp of the scaled distance itself: weight G_ik / h (0 at h == 0)
     int tile_off;     // sym mode: index of the first lower tile visited (row-range restricted contraction)
     double* partial;  // [nblocks][2 + d]
+    // batched form (blockIdx.z = entry): per-entry kernel parameters and element strides
+    const MaternDev* mdev; long long strideG, strideU, strideX;
 };
 
 template <int P>
@@ -409,17 +413,20 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
     __shared__ __align__(16) double ys[GPMP_MAX_DIM][CT];
     __shared__ double wacc[COV_THREADS / 32][GPMP_MAX_DIM + 2];
     __shared__ MaternDev msh;
-    stage_matern(&msh, nullptr, a.m);
+    stage_matern(&msh, a.mdev ? a.mdev + blockIdx.z : nullptr, a.m);
     const MaternDev& m = msh;
     MaternRegs<P> mr;
     mr.init(&msh);
+    const long long zb = blockIdx.z;
+    const double* __restrict__ Gz = a.G + zb * a.strideG;
+    const double* __restrict__ Uz = a.Ut ? a.Ut + zb * a.strideU : nullptr;
     int ti, tj;
     if (a.sym) tri_decode(blockIdx.x + a.tile_off, ti, tj);
     else { ti = blockIdx.x / a.tiles_n; tj = blockIdx.x - ti * a.tiles_n; }
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
     const int r0 = ti * CT, c0 = tj * CT;
-    stage_points(xs, a.x, r0, a.n, m, tid);
-    stage_points(ys, a.y, c0, a.mcols, m, tid);
+    stage_points(xs, a.x + zb * a.strideX, r0, a.n, m, tid);
+    stage_points(ys, a.y + zb * a.strideX, c0, a.mcols, m, tid);
     __syncthreads();
 
     double h2[4][4];
@@ -459,8 +466,8 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
                 if (col < row) mult = 2.0;
             }
             if (live) {
-                gv = a.G[(long long)row * a.ldg + col];
-                for (int q = 0; q < a.r; ++q) gv -= a.Ut[(long long)q * a.ldu + row] * a.Ut[(long long)q * a.ldu + col];
+                gv = Gz[(long long)row * a.ldg + col];
+                for (int q = 0; q < a.r; ++q) gv -= Uz[(long long)q * a.ldu + row] * Uz[(long long)q * a.ldu + col];
             }
             const double h = fast_sqrt(h2[i][k]);
             double dkh, kc;
@@ -504,7 +511,7 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
         double t = 0.0;
 #pragma unroll
         for (int wv = 0; wv < COV_THREADS / 32; ++wv) t += wacc[wv][tid];
-        a.partial[(long long)blockIdx.x * (2 + m.d) + tid] = t;
+        a.partial[((long long)blockIdx.z * gridDim.x + blockIdx.x) * (2 + m.d) + tid] = t;
     }
 }
 
@@ -513,26 +520,30 @@ struct ContractFinalArgs {
     const double* partial; long long nblocks; int d, noise;
     double diag_add, half;  // half = 0.5 for the likelihood (0.5 tr(M dK)), 1.0 for a plain vjp
     double* grad;           // [1 + noise + d]
+    const MaternDev* mdev;  // batched form: one block per entry, diag_add from the entry's parameters
 };
 __global__ void contract_final_kernel(const ContractFinalArgs a) {
     __shared__ double red[40];
     const int nv = 2 + a.d;
     __shared__ double tot[GPMP_MAX_DIM + 2];
+    const double* __restrict__ partial = a.partial + (long long)blockIdx.x * a.nblocks * nv;
+    double* __restrict__ grad = a.grad + (long long)blockIdx.x * (1 + a.noise + a.d);
+    const double diag_add = a.mdev ? a.mdev[blockIdx.x].diag_add : a.diag_add;
     for (int v = 0; v < nv; ++v) {
         double s = 0.0;
-        for (long long b = threadIdx.x; b < a.nblocks; b += blockDim.x) s += a.partial[b * nv + v];
+        for (long long b = threadIdx.x; b < a.nblocks; b += blockDim.x) s += partial[b * nv + v];
         s = block_sum(s, red);
         if (threadIdx.x == 0) tot[v] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (a.noise) {
-            a.grad[0] = a.half * tot[0];
-            a.grad[1] = a.half * a.diag_add * tot[1];
+            grad[0] = a.half * tot[0];
+            grad[1] = a.half * diag_add * tot[1];
         } else {
-            a.grad[0] = a.half * (tot[0] + a.diag_add * tot[1]);
+            grad[0] = a.half * (tot[0] + diag_add * tot[1]);
         }
-        for (int j = 0; j < a.d; ++j) a.grad[1 + a.noise + j] = a.half * tot[2 + j];
+        for (int j = 0; j < a.d; ++j) grad[1 + a.noise + j] = a.half * tot[2 + j];
     }
 }
 
@@ -544,8 +555,10 @@ size_t contract_workspace_bytes(int n, int mcols, int d) {
 int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const double* y, int mcols, const double* G,
                     long long ldg, const double* Ut, long long ldu, int r, int sym, int dist_only, double half,
                     double* grad, void* partial, size_t partial_bytes, cudaStream_t stream, int tile_row0,
-                    int tile_row1) {
+                    int tile_row1, const ContractBatch* cb) {
     const bool same = (y == nullptr || y == x);
+    const int batch = cb ? cb->batch : 1;
+    if (batch <= 0) return GPMP_OK;
     if (sym && !same) return GPMP_ERR_ARG;
     if (r > CONTRACT_MAXR) return GPMP_ERR_ARG;
     ContractArgs a;
@@ -566,27 +579,30 @@ int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const dou
         a.tile_off = (int)((long long)tile_row0 * (tile_row0 + 1) / 2);
         nblocks = (long long)tile_row1 * (tile_row1 + 1) / 2 - a.tile_off;
     }
-    if ((size_t)nblocks * (2 + spec->d) * sizeof(double) > partial_bytes) return GPMP_ERR_WORKSPACE;
+    if ((size_t)nblocks * batch * (2 + spec->d) * sizeof(double) > partial_bytes) return GPMP_ERR_WORKSPACE;
     a.partial = static_cast<double*>(partial);
+    a.mdev = cb ? cb->mdev : nullptr;
+    a.strideG = cb ? cb->strideG : 0; a.strideU = cb ? cb->strideU : 0; a.strideX = cb ? cb->strideX : 0;
+    const dim3 cgrid((unsigned)nblocks, 1, (unsigned)batch);
     {
         double bytes = sym ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
         LaunchScope scope(KC_CONTRACT, bytes, stream);
         if (nblocks > 0) switch (dist_only ? 0 : spec->p) {
-            case 0: contract_kernel<0><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
-            case 1: contract_kernel<1><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
-            case 2: contract_kernel<2><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
-            case 3: contract_kernel<3><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
-            case 4: contract_kernel<4><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
-            default: contract_kernel<-1><<<(unsigned)nblocks, COV_THREADS, 0, stream>>>(a); break;
+            case 0: contract_kernel<0><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
+            case 1: contract_kernel<1><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
+            case 2: contract_kernel<2><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
+            case 3: contract_kernel<3><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
+            case 4: contract_kernel<4><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
+            default: contract_kernel<-1><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
         }
         GPMP_CHECK_LAUNCH();
     }
     ContractFinalArgs f;
     f.partial = a.partial; f.nblocks = nblocks; f.d = spec->d; f.noise = spec->noise;
-    f.diag_add = a.m.diag_add; f.half = half; f.grad = grad;
+    f.diag_add = a.m.diag_add; f.half = half; f.grad = grad; f.mdev = a.mdev;
     {
         LaunchScope scope(KC_SMALL, 0.0, stream);
-        contract_final_kernel<<<1, 256, 0, stream>>>(f);
+        contract_final_kernel<<<batch, 256, 0, stream>>>(f);
         GPMP_CHECK_LAUNCH();
     }
     return GPMP_OK;

@@ -1576,12 +1576,13 @@ struct CopyDiagArgs {
     const double* slo; const double* sup; int NB;  // compact blocks (ld NB)
     double* dlo; double* dup; long long ld;        // full matrices
     int n;
+    long long strideS, strideD;                    // batch strides (blockIdx.z) of the compact / full matrices
 };
 __global__ void copy_diag_blocks_kernel(const CopyDiagArgs a) {
     const int b = blockIdx.y;
     const int nbk = min(a.NB, a.n - b * a.NB);
-    const long long src0 = (long long)b * a.NB * a.NB;
-    const long long dst0 = (long long)b * a.NB * (a.ld + 1);
+    const long long src0 = (long long)blockIdx.z * a.strideS + (long long)b * a.NB * a.NB;
+    const long long dst0 = (long long)blockIdx.z * a.strideD + (long long)b * a.NB * (a.ld + 1);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)nbk * nbk;
          e += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(e / nbk), c = (int)(e - (long long)r * nbk);
@@ -1591,27 +1592,32 @@ __global__ void copy_diag_blocks_kernel(const CopyDiagArgs a) {
 }
 
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
-               double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream) {
-    if (n <= 0) return GPMP_OK;
+               double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream, int batch,
+               long long strideL, long long strideTc, long long strideT) {
+    // batched form: entry b reads L + b strideL and the compact inverses + b strideTc, and writes Tlo / Tup / Kinv
+    // + b strideT (all three share one stride)
+    if (n <= 0 || batch <= 0) return GPMP_OK;
     int rc;
     const int nblk = ceil_div(n, NB);
     {
         CopyDiagArgs c;
         c.slo = Tlo_c; c.sup = Tup_c; c.NB = NB; c.dlo = Tlo; c.dup = Tup; c.ld = ldk; c.n = n;
+        c.strideS = strideTc; c.strideD = strideT;
         LaunchScope scope(KC_SMALL, 0.0, stream);
-        dim3 grid(min(64, ceil_div(NB * NB, 256)), nblk);
+        dim3 grid(min(64, ceil_div(NB * NB, 256)), nblk, batch);
         copy_diag_blocks_kernel<<<grid, 256, 0, stream>>>(c);
         GPMP_CHECK_LAUNCH();
     }
     // doubling NB -> n; scratch for X^T: the Kinv buffer (written only by the final product)
     for (long long s = NB; s < n; s *= 2) {
-        rc = doubling_level(L, ldl, 0, Tlo, Tup, ldk, 0, Kinv, ldk, 0, n, (int)s, 1, stream);
+        rc = doubling_level(L, ldl, strideL, Tlo, Tup, ldk, strideT, Kinv, ldk, strideT, n, (int)s, batch, stream);
         if (rc) return rc;
     }
     // Kinv (lower) = T^T T :  Kinv_ij = sum_{k >= i} Tup[i][k] Tup[j][k]
     GemmDesc g = gemm_desc();
-    g.A = Tup; g.lda = ldk; g.B = Tup; g.ldb = ldk; g.C = Kinv; g.ldc = ldk;
-    g.M = n; g.N = n; g.K = n; g.lower = 1; g.krange = KR_FROM_ROW;
+    g.A = Tup; g.lda = ldk; g.strideA = strideT; g.B = Tup; g.ldb = ldk; g.strideB = strideT;
+    g.C = Kinv; g.ldc = ldk; g.strideC = strideT;
+    g.M = n; g.N = n; g.K = n; g.lower = 1; g.krange = KR_FROM_ROW; g.batch = batch;
     return launch_gemm_nt(g, stream);
 }
 

@@ -29,14 +29,15 @@ def shard_bounds(N, group=None):
 
 
 def all_gather_rows(local, N, group=None):
-    """Concatenate the ranks' blocks (block_bounds layout) of a 1-D tensor into the full length-N tensor."""
+    """Concatenate the ranks' blocks (block_bounds layout) of a tensor whose first dimension is sharded
+    (values: 1-D; gradient rows: 2-D) into the full tensor with N rows."""
     rank, size = world(group)
     if size == 1:
         return local
     base, rem = divmod(N, size)
     width = base + (1 if rem else 0)
-    pad = torch.zeros(width, dtype=local.dtype, device=local.device)
-    pad[: local.numel()] = local
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
     parts = [torch.empty_like(pad) for _ in range(size)]
     td.all_gather(parts, pad, group=group)
     chunks = []

@@ -674,3 +674,45 @@ def criterion_batched(theta, x, z, P, p, noise=False, max_bytes=None, work=None)
                                        work.numel(), ptr(values), ptr(info), stream_ptr()),
           "gpmp_criterion_batched")
     return values, info[:N]
+
+
+def criterion_batched_grad_workspace(n, q, d, N, max_bytes=None):
+    """Workspace for up to N entries of the batched value+gradient pipeline in flight (default cap 16 GiB)."""
+    if max_bytes is None:
+        max_bytes = 16 << 30
+    per1 = lib().gpmp_criterion_batched_grad_bytes(n, q, d, 1)
+    per2 = lib().gpmp_criterion_batched_grad_bytes(n, q, d, 2) - per1
+    nb = max(1, min(max(N, 1), (max_bytes - per1) // max(per2, 1) + 1))
+    return _workspace(lib().gpmp_criterion_batched_grad_bytes(n, q, d, int(nb)))
+
+
+def criterion_batched_grad(theta, x, z, P, p, noise=False, max_bytes=None, work=None):
+    """N criterion values and gradients in one call.  theta: (N, 1+noise+d); x: (n, d) shared points or
+    (N, n, d) one point set per entry; z: (n,) or (N, n) likewise; P: (n, q) shared basis or None.
+    Returns device tensors (values[N], grads[N, 1+noise+d], info[N]); gradient rows of entries that are not
+    positive definite are zeroed (torch_backend.py:528-529)."""
+    N = theta.shape[0]
+    per_entry_x = x.dim() == 3
+    n, d = x.shape[-2], x.shape[-1]
+    if per_entry_x and x.shape[0] != N:
+        raise _abi.GpmpError(f"x has {x.shape[0]} point sets for {N} parameter rows")
+    per_entry_z = z.dim() == 2
+    if per_entry_z and z.shape[0] != N:
+        raise _abi.GpmpError(f"z has {z.shape[0]} rows for {N} parameter rows")
+    q = 0 if P is None else P.shape[1]
+    spec = _abi.make_spec(p, d, 0.0, [0.0] * d, noise=noise)
+    width = 1 + int(bool(noise)) + d
+    values, grads = _empty((N,)), _empty((N, width))
+    info = torch.empty(max(N, 1), dtype=torch.int32, device=device())
+    if N == 0:
+        return values, grads, info[:0]
+    x, z = x.contiguous(), z.contiguous()
+    if work is None:
+        work = criterion_batched_grad_workspace(n, q, d, N, max_bytes)
+    check(lib().gpmp_criterion_batched_grad(C.byref(spec), ptr(theta.contiguous()), N, ptr(x),
+                                            n * d if per_entry_x else 0, n, ptr(z), n if per_entry_z else 0,
+                                            ptr(P), q, ptr(work), work.numel(), ptr(values), ptr(grads), ptr(info),
+                                            stream_ptr()), "gpmp_criterion_batched_grad")
+    info = info[:N]
+    grads = torch.where((info != 0).reshape(-1, 1), torch.zeros_like(grads), grads)
+    return values, grads, info

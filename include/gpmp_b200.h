@@ -247,6 +247,21 @@ int gpmp_criterion_batched(const gpmp_cov_spec* spec, const double* theta_dev, i
                            int n, const double* z_dev, const double* P_dev, int q, void* work_dev,
                            size_t work_bytes, double* values_dev, int* info_dev, void* stream);
 
+/* ---- batched criterion WITH gradients: N independent values and d value / d theta rows in one call.
+ * Replaces the per-particle value-and-gradient loop of gpmp/mcmc/svgd.py:310-313 (gnp.value_and_grad per
+ * particle) and the per-batch loop of BatchDifferentiableSelectionCriterion.evaluate_pre_grad
+ * (gpmp/num/torch_backend.py:686-712).  Entry b uses theta_b (row b of theta_dev), the points
+ * x_dev + b * x_stride and the observations z_dev + b * z_stride (strides in doubles; 0 = all entries share
+ * the data: particles; n*d / n = consecutive mini-batches of n points); the mean basis P_dev (n x q, may be
+ * NULL for q = 0) is shared.  values_dev[N], grads_dev[N x (1+noise+d)], info_dev[N].  Entries whose matrix is
+ * not positive definite get value +inf and an undefined gradient row (the caller zeroes it, like
+ * gpmp/num/torch_backend.py:528-529).  work_bytes >= gpmp_criterion_batched_grad_bytes(n, q, d, 1). */
+size_t gpmp_criterion_batched_grad_bytes(int n, int q, int d, int nbatch);
+int gpmp_criterion_batched_grad(const gpmp_cov_spec* spec, const double* theta_dev, int N, const double* x_dev,
+                                long long x_stride, int n, const double* z_dev, long long z_stride,
+                                const double* P_dev, int q, void* work_dev, size_t work_bytes,
+                                double* values_dev, double* grads_dev, int* info_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,11 @@ def _worker(rank, world, port, N, q):
     lo, hi = gdist.shard_bounds(N)
     local = torch.arange(lo, hi, dtype=torch.float64) ** 2  # stands for the rank's criterion values
     full = gdist.all_gather_rows(local, N)
+    # gradient rows (2-D, first dimension sharded) travel the same way
+    rows = torch.stack([torch.arange(lo, hi, dtype=torch.float64), -torch.arange(lo, hi, dtype=torch.float64)], dim=1)
+    full_rows = gdist.all_gather_rows(rows, N)
+    assert full_rows.shape == (N, 2) and torch.equal(full_rows[:, 0], torch.arange(N, dtype=torch.float64))
+    assert torch.equal(full_rows[:, 1], -torch.arange(N, dtype=torch.float64))
     q.put((rank, lo, hi, full.tolist()))
     dist.destroy_process_group()
 
