@@ -11,6 +11,8 @@ static ProfState g_prof = {};
 struct EvPair { cudaEvent_t a, b; };
 static std::vector<EvPair> g_events[KC_COUNT];
 static std::vector<cudaEvent_t> g_pool;
+struct TimelineEntry { int cls; size_t idx; cudaStream_t stream; };
+static std::vector<TimelineEntry> g_timeline;  // launch order across classes (development timeline dump)
 
 ProfState& prof() { return g_prof; }
 static cudaEvent_t get_event() {
@@ -30,6 +32,7 @@ void prof_begin(int cls, cudaStream_t s) {
     p.a = get_event();
     p.b = get_event();
     cudaEventRecord(p.a, s);
+    g_timeline.push_back({cls, g_events[cls].size(), s});
     g_events[cls].push_back(p);
 }
 void prof_end(int cls, double work, cudaStream_t s) {
@@ -105,8 +108,33 @@ int gpmp_prof_enable(int enable) {
     g_prof.enabled = enable ? 1 : 0;
     return GPMP_OK;
 }
+// development hook (not part of the header): rows [class, stream id, start ms, duration ms] of every launch
+// recorded since profiling was enabled, in launch order; call before gpmp_prof_read (which recycles the events)
+int gpmp_debug_timeline(double* out, int max_rows) {
+    if (g_timeline.empty()) return 0;
+    std::vector<cudaStream_t> streams;
+    const EvPair& first = g_events[g_timeline[0].cls][g_timeline[0].idx];
+    int n = 0;
+    for (auto& t : g_timeline) {
+        if (n >= max_rows) break;
+        const EvPair& p = g_events[t.cls][t.idx];
+        if (cudaEventSynchronize(p.b) != cudaSuccess) return -1;
+        float st = 0.f, du = 0.f;
+        cudaEventElapsedTime(&st, first.a, p.a);
+        cudaEventElapsedTime(&du, p.a, p.b);
+        size_t sid = 0;
+        for (; sid < streams.size(); ++sid)
+            if (streams[sid] == t.stream) break;
+        if (sid == streams.size()) streams.push_back(t.stream);
+        out[4 * n + 0] = t.cls; out[4 * n + 1] = (double)sid; out[4 * n + 2] = st; out[4 * n + 3] = du;
+        ++n;
+    }
+    return n;
+}
+
 int gpmp_prof_read(int cls, double* ms, unsigned long long* launches, double* work) {
     if (cls < 0 || cls >= KC_COUNT) return GPMP_ERR_ARG;
+    g_timeline.clear();
     double total = 0.0;
     for (auto& p : g_events[cls]) {
         if (cudaEventSynchronize(p.b) != cudaSuccess) return GPMP_ERR_CUDA;
