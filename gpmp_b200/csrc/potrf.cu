@@ -24,8 +24,8 @@
 namespace gpmp {
 
 constexpr int PT = 128;          // base tile
-constexpr int PLD = 130;         // smem leading dimension of the tile (even: rows stay 16-byte aligned)
-constexpr int XLD = 66;          // smem leading dimension of the scratch
+constexpr int PLD = 132;         // smem leading dimension of the tile (4 mod 16: conflict-free DMMA fragment loads)
+constexpr int XLD = 68;          // smem leading dimension of the scratch (4 mod 16)
 constexpr int POTF2_THREADS = 512;
 constexpr int POTF2_SMEM = (PT * PLD + 96 * XLD + PT) * 8;
 // Packed lower tile: block row b (32 rows) keeps its 32 (b + 1) leading columns with leading dimension
