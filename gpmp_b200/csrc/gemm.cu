@@ -254,6 +254,15 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
     // panel solves, A == C) must keep one column tile per row block, so N > 64 takes the 128-wide shape.
     const bool in_place = (g.A == g.C || g.B == g.C);
     if (in_place && g.N > 64) return launch_cfg<4, 4, 4, 4, 1>(g, stream);
+    // Latency shapes for launches that cannot fill the machine (the chain's K=128 updates in the tail of a
+    // factorisation): a lone 64x64 tile costs 5 us + 0.8 us per 16-wide k step because one warp per scheduler
+    // partition issues all its DMMAs; 32-row / 32x32 tiles spread the same work over 2x / 4x the SMs.
+    if (!in_place && g.batch == 1 && g.batch2 == 1) {
+        const long long tm = ceil_div(g.M, 64), tn = ceil_div(g.N, 64);
+        const long long t64 = g.lower ? (tn < tm ? tn * (tn + 1) / 2 + (tm - tn) * tn : tm * (tm + 1) / 2) : tm * tn;
+        if (t64 <= (g.lower ? 296 : 148)) return launch_cfg<2, 2, 2, 2, 8, 3, 1>(g, stream);
+        if (t64 <= 296 && !g.lower) return launch_cfg<2, 2, 2, 4, 6, 3, 1>(g, stream);  // (lower lists need square tiles)
+    }
     return launch_cfg<2, 2, 4, 4, 4, 3, 1>(g, stream);
 }
 
