@@ -454,6 +454,27 @@ def test_batched_value_and_grad(gp, case):
     assert np.array_equal(v2, vals) and np.array_equal(g2, grads)
 
 
+@pytest.mark.parametrize("n,d,p,kind,noise", [(257, 2, 0, "const", False), (130, 5, 4, "linear", False),
+                                              (300, 3, 2, "const", True), (64, 2, 1, "zero", False),
+                                              (513, 4, 10, "const", False)])
+def test_batched_value_and_grad_variants(gp, n, d, p, kind, noise):
+    """Ragged sizes, p = 0 / 4 / generic (10), a linear basis (q = d + 1 rows in the panels), the noisy kernel
+    (gradient w.r.t. log tau2) and the zero-mean form: batched rows == the scalar value_and_grad."""
+    x, z, _ = cases.data(n, d, 90 + n)
+    th0 = cases.theta(d, 90 + n, noise=noise)
+    N = 5
+    TH = th0 + np.random.default_rng(n).uniform(-0.5, 0.5, size=(N, th0.shape[0]))
+    m = _model(gp, kind, p, noise, th0)
+    crit = gp.batched.BatchedCriterion(m, x, z, p, kind="ml" if kind == "zero" else "reml", noise=noise)
+    vals, grads = crit.value_and_grad(TH)
+    assert grads.shape == (N, th0.shape[0])
+    f = m.negative_log_likelihood_zero_mean if kind == "zero" else m.negative_log_restricted_likelihood
+    for i in range(N):
+        v, gi = gp.num.value_and_grad(lambda t: f(t, x, z), TH[i])
+        assert relerr(vals[i], float(v)) <= 1e-9, (i, vals[i], float(v))
+        assert relerr_norm(grads[i], gi.cpu().numpy()) <= 1e-8, (i, grads[i], gi)
+
+
 def test_batched_value_and_grad_not_pd(gp):
     """A particle whose matrix is not positive definite: +inf value, zero gradient row, neighbours untouched."""
     x, z, _ = cases.data(150, 2, 60)
