@@ -249,6 +249,7 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
     //   64x64 tiles, 4 warps, 3 stages x 16 k (48 KB), 4 CTAs/SM      24.1 / 30.9 / 32.8   <- default
     //   64x64 tiles, 4 warps, 4 stages x 16 k (64 KB), 3 CTAs/SM      21.3 / 30.5 / 32.9
     //   128x128 tiles, 16 warps, 3 stages x 32 k (192 KB), 1 CTA/SM   18.5 / 25.8 / 32.0
+    //   32x64 / 64x32 / 32x32 tiles, 4 warps, 6-8 CTAs/SM (8192^3)     29.0 / 30.3 / 25.8
     // Several independent CTAs per SM hide each other's barrier and fragment-load bubbles, which a single
     // big CTA cannot (the DMMA pipe sat at 85 % with 1 CTA/SM).  An in-place product (the single-column-tile
     // panel solves, A == C) must keep one column tile per row block, so N > 64 takes the 128-wide shape.
