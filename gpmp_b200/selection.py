@@ -109,8 +109,9 @@ def autoselect_parameters(p0, criterion, gradient, bounds=None, bounds_auto=True
 
     options = {"disp": not silent}
     if method == "L-BFGS-B":
-        options.update(dict(maxcor=20, ftol=1e-6, gtol=1e-5, eps=1e-8, maxfun=15000, maxiter=15000, maxls=40,
-                            iprint=-1))
+        # the reference also passes disp / iprint=-1 (parameter_selection.py:236-247); current SciPy has dropped
+        # both for this solver and only warns about them, so they are left out
+        options = dict(maxcor=20, ftol=1e-6, gtol=1e-5, eps=1e-8, maxfun=15000, maxiter=15000, maxls=40)
     elif method == "SLSQP":
         options.update(dict(ftol=1e-6, eps=1e-8, maxiter=15000))
     else:

@@ -88,3 +88,55 @@ def test_build_entry_point():
 
     g.build()
     assert os.path.exists(os.path.join(ROOT, "gpmp_b200", "libgpmp_b200.so"))
+
+
+# ---- host-side selection driver (gpmp_b200/selection.py; mirrors kernel/parameter_selection.py:128-276) ----------
+def test_autoselect_parameters_driver_on_a_quadratic():
+    """The SciPy loop around a criterion: bounds, history, best-seen tracking and the info fields the samplers
+    read -- exercised on a closed-form criterion (no device needed)."""
+    from gpmp_b200 import selection
+
+    target = np.array([0.5, -1.5, 2.0])
+
+    def crit(p):
+        return float(np.sum((np.asarray(p) - target) ** 2) + 3.0)
+
+    def grad(p):
+        return 2.0 * (np.asarray(p) - target)
+
+    p0 = np.zeros(3)
+    for method in ("SLSQP", "L-BFGS-B"):
+        best, info = selection.autoselect_parameters(p0, crit, grad, info=True, method=method)
+        assert np.allclose(best, target, atol=1e-4) and abs(info.fun - 3.0) <= 1e-6
+        assert len(info["history_params"]) == len(info["history_criterion"]) >= 2
+        assert np.array_equal(info["initial_params"], p0) and np.allclose(info["final_params"], best)
+        assert info["bounds"] == [(-10.0, 10.0)] * 3 and info["total_time"] >= 0.0
+    # explicit bounds are honoured; automatic bounds are clipped to +-500
+    best, _ = selection.autoselect_parameters(p0, crit, grad, bounds=[(-1, 0.2), (-1, 1), (0, 1)])
+    assert np.allclose(best, [0.2, -1.0, 1.0], atol=1e-6)
+    _, info = selection.autoselect_parameters(np.array([495.0]), lambda p: float((p[0] - 490.0) ** 2),
+                                              lambda p: 2.0 * (np.asarray(p) - 490.0), info=True)
+    assert info["bounds"] == [(485.0, 500.0)]
+    with pytest.raises(ValueError):
+        selection.autoselect_parameters(p0, crit, grad, method="Nelder-Mead")
+
+
+def test_autoselect_parameters_maps_linear_algebra_failures_to_inf():
+    """A criterion that raises a linear-algebra error on part of the domain counts as +inf there
+    (parameter_selection.py:222-231); any other exception propagates."""
+    from gpmp_b200 import selection
+
+    def crit(p):
+        if p[0] > 1.0:
+            raise torch.linalg.LinAlgError("not positive definite")
+        return float((p[0] - 0.9) ** 2)
+
+    best, info = selection.autoselect_parameters(np.array([0.0]), crit, lambda p: 2.0 * (np.asarray(p) - 0.9),
+                                                 info=True)
+    assert abs(best[0] - 0.9) <= 1e-3 and np.isfinite(info["history_criterion"]).any()
+
+    def broken(p):
+        raise KeyError("unrelated")
+
+    with pytest.raises(KeyError):
+        selection.autoselect_parameters(np.array([0.0]), broken, lambda p: np.zeros(1))
