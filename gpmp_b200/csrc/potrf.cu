@@ -832,6 +832,8 @@ struct TrsmTileArgs {
     int blocks_per_cta;   // consecutive 64-row blocks walked by one CTA
     int inplace_from;     // rows below this index are not written back into A (value-only batched runs need
                           // only the panel buffer for them)
+    int block_rows;       // rows per block: 64, or 32 for launches with few blocks (half the work per CTA, twice
+                          // the CTAs: the chain's solves are latency-bound)
     double* E;            // optional extra rows at the tile's columns (E[i * lda + c], same strideA): solved in
     int nextra;           // place; their columns right of the tile (E + nb + r) receive -X_E X_r^T for every row r
 };
@@ -856,7 +858,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
     const int blk0 = blockIdx.x * a.blocks_per_cta;
     const int nextra = a.E ? a.nextra : 0;
     double* __restrict__ E = a.E ? a.E + zb * a.strideA : nullptr;
-    int nblocks = min(a.blocks_per_cta, ceil_div(a.M, TS_ROWS) - blk0);
+    const int R = a.block_rows, rshift = R == 64 ? 6 : 5;
+    int nblocks = min(a.blocks_per_cta, ceil_div(a.M, R) - blk0);
     if (nblocks <= 0) {
         if (nextra == 0 || blockIdx.x != 0) return;
         nblocks = 1;  // no rows below the tile: one pass for the extra rows only
@@ -865,8 +868,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
     // stage the rows of one block into this half's buffer (16-byte async copies, zero fill beyond M / nb)
     auto stage_rows = [&](int blk) {
         const uint32_t xb = smem_u32(Xs);
-        const int r0 = blk * TS_ROWS;
-        for (int e = htid; e < TS_ROWS * (PT / 2); e += TS_HALF_THREADS) {
+        const int r0 = blk * R;
+        for (int e = htid; e < R * (PT / 2); e += TS_HALF_THREADS) {
             const int r = e >> 6, c = (e & 63) * 2;
             int bytes = 0;
             if (r0 + r < a.M) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
     bool first = true;
     for (int it = half; it < nblocks || first; it += 2) {
         const bool live = it < nblocks;
-        const int r0 = (blk0 + it) * TS_ROWS;
+        const int r0 = (blk0 + it) * R;
         if (live) {
             if (!first) {
                 stage_rows(blk0 + it);
@@ -987,14 +990,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
                 cp_async_wait<0>();
                 half_barrier(half);
             }
-            solve_strip(Xs + (hw * 8 + gq) * TS_LD);
+            if (hw * 8 < R) solve_strip(Xs + (hw * 8 + gq) * TS_LD);
         }
         if (first) __syncthreads();  // the extra strip is solved (every warp passes here exactly once)
         else half_barrier(half);
         first = false;
         if (!live) break;
         // write out: panel buffer + A in place (rows of this block), then the mirrored upper tiles
-        for (int e = htid; e < TS_ROWS * (PT / 2); e += TS_HALF_THREADS) {
+        for (int e = htid; e < R * (PT / 2); e += TS_HALF_THREADS) {
             const int r = e >> 6, c = (e & 63) * 2;
             if (r0 + r >= a.M || c >= nb) continue;
             const double v0 = Xs[r * TS_LD + c], v1 = Xs[r * TS_LD + c + 1];
@@ -1011,12 +1014,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) trsm_tile_kernel(const TrsmTile
         }
         if (a.Aup && r0 < a.mirror_rows) {
             double* __restrict__ Aup = a.Aup + zb * a.strideA;
-            for (int e = htid; e < PT * TS_ROWS; e += TS_HALF_THREADS) {
-                const int j = e >> 6, r = e & 63;  // consecutive threads -> consecutive rows r: contiguous in Aup
+            for (int e = htid; e < PT * R; e += TS_HALF_THREADS) {
+                const int j = e >> rshift, r = e & (R - 1);  // consecutive threads -> consecutive rows r: contiguous in Aup
                 if (j < nb && r0 + r < a.mirror_rows) Aup[(long long)j * a.lda + r0 + r] = Xs[r * TS_LD + j];
             }
         }
-        if (nextra && r0 + hw * 8 < a.M) {
+        if (nextra && hw * 8 < R && r0 + hw * 8 < a.M) {
             // extra rows: their part right of the tile, columns of this block:  E[i][nb + r0 + r] -= X_E[i] . X[r]
             // one 8x8 output tile per warp (rows = extra rows, columns = the warp's own strip), K = 128 on DMMA
             const double* er = Es + gq * TS_LD + kk;
@@ -1060,7 +1063,8 @@ static int launch_trsm_tile(TrsmTileArgs a, int batch, cudaStream_t stream) {
     }
     LaunchScope scope(KC_GEMM, 2.0 * (double)a.M * PT * PT * batch, stream);
     // enough CTAs for two per SM (148 SMs); beyond that every CTA walks several row blocks of its matrix
-    const int nblocks = max(1, ceil_div(a.M, TS_ROWS));
+    a.block_rows = (batch == 1 && a.nextra == 0 && ceil_div(a.M, TS_ROWS) <= 148) ? 32 : TS_ROWS;
+    const int nblocks = max(1, ceil_div(a.M, a.block_rows));
     // (one CTA per matrix when it carries extra rows: it rewrites them in place)
     const int splits = a.nextra > 0 ? 1 : min(nblocks, max(1, ceil_div(2 * 148, batch)));
     a.blocks_per_cta = ceil_div(nblocks, splits);
