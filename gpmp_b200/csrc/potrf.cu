@@ -182,6 +182,21 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
     __syncthreads();
 
     POTF2_STAMP(1);
+    const bool vec = ((a.lda & 1) == 0) && ((a.ldt & 1) == 0);
+    if (a.mode == POTF2_FACTOR) {
+        // factor-only (the chain): the explicit zeros of the strict upper part do not depend on the factor,
+        // so they leave now, under the pivot chain, instead of lengthening the write-back at the end
+        for (int e = tid; e < PT * (PT / 2); e += POTF2_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            if (r >= nb || c >= nb || c <= r) continue;  // chunks wholly above the diagonal
+            double* dst = A + (long long)r * a.lda + c;
+            if (vec && c + 1 < nb) *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+            else {
+                dst[0] = 0.0;
+                if (c + 1 < nb) dst[1] = 0.0;
+            }
+        }
+    }
     int bad = 0;  // 1-based local index of the first non-positive pivot (warp 0, lane 0 only)
     if (a.mode == POTF2_INVERT) {
         if (tid < PT) rinv[tid] = 1.0 / S[tid * PLD + tid];
@@ -455,10 +470,13 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
 
     // ---- write back: L (lower, zero upper) into A; T into Tlo (lower) / Tup (upper) -------------
     // two columns per thread and step: 16-byte stores when the row is even-aligned and fully live
-    const bool vec = ((a.lda & 1) == 0) && ((a.ldt & 1) == 0);
+    const bool factor_only = a.mode == POTF2_FACTOR;
     for (int e = tid; e < PT * (PT / 2); e += POTF2_THREADS) {
         const int r = e >> 6, c = (e & 63) * 2;
         if (r >= nb || c >= nb) continue;
+        // factor-only: the zeros are already written and T is needed on its diagonal 32-blocks only (those
+        // include the zeros above their diagonals, which the substitution solve reads)
+        if (factor_only && c > r && (r >> 5) != (c >> 5)) continue;
         const double l0 = c <= r ? S[r * PLD + c] : 0.0;
         const double l1 = c + 1 <= r ? S[r * PLD + c + 1] : 0.0;
         double* dst = A + (long long)r * a.lda + c;
@@ -467,7 +485,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
             dst[0] = l0;
             if (c + 1 < nb) dst[1] = l1;
         }
-        if (a.Tlo) {
+        if (a.Tlo && (!factor_only || (r >> 5) == (c >> 5))) {
             double* __restrict__ Tlo = a.Tlo + zb * a.strideT + (long long)r * a.ldt + c;
             double* __restrict__ Tup = a.Tup ? a.Tup + zb * a.strideT + (long long)r * a.ldt + c : nullptr;
             // T[r][c] lives at S[c][r] (r > c); T^T[r][c] = T[c][r] lives at S[r][c] (c > r)
