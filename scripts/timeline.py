@@ -14,8 +14,19 @@ spec = _abi.make_spec(2, x.shape[1], th0[0], th0[1:])
 for _ in range(3):
     ops.lik_value(spec, None, xd, zd, P, False)
 torch.cuda.synchronize()
+want_grad = len(sys.argv) > 4 and sys.argv[4] == "grad"
+if want_grad:
+    st, _ = ops.lik_value(spec, None, xd, zd, P, True)
+    ops.lik_grad(st, False, False)
+    torch.cuda.synchronize()
 _abi.prof_enable(True)
-ops.lik_value(spec, None, xd, zd, P, False)
+if want_grad:
+    st, _ = ops.lik_value(spec, None, xd, zd, P, True)
+    torch.cuda.synchronize()
+    _abi.prof_enable(False); [_abi.prof_read(c) for c in range(6)]; _abi.prof_enable(True)
+    ops.lik_grad(st, False, False)
+else:
+    ops.lik_value(spec, None, xd, zd, P, False)
 torch.cuda.synchronize()
 lib = _abi.lib()
 buf = (C.c_double * (4 * 4000))()
