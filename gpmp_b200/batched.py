@@ -94,6 +94,55 @@ class BatchedCriterion:
         return out
 
 
+    # ------------------------------------------------------------------ grid clients (model diagnosis)
+    def cross_sections(self, param_opt, ind=None, n_points=100, delta=5.0, param_box=None):
+        """Criterion along each coordinate through `param_opt` -- the data of
+        `plot_selection_criterion_crosssections` (gpmp/modeldiagnosis/plotting.py:72-231, same defaults):
+        for parameter ind[a] the grid runs over [opt - delta, opt + delta] or over
+        [param_box[0, a], param_box[1, a]].  All len(ind) * n_points evaluations go through one batched
+        sweep instead of a Python loop.  Returns {param_index: (grid[n_points], values[n_points])}."""
+        opt = np.asarray(param_opt, dtype=np.float64).reshape(-1)
+        ind = list(range(opt.shape[0])) if ind is None else list(ind)
+        grids, rows = [], []
+        for a, j in enumerate(ind):
+            if param_box is not None:
+                lo, hi = float(np.asarray(param_box)[0, a]), float(np.asarray(param_box)[1, a])
+            else:
+                lo, hi = float(opt[j]) - float(delta), float(opt[j]) + float(delta)
+            g = np.linspace(lo, hi, int(n_points))
+            th = np.tile(opt, (int(n_points), 1))
+            th[:, j] = g
+            grids.append(g)
+            rows.append(th)
+        vals = self(np.concatenate(rows)) if rows else np.zeros(0)
+        return {j: (grids[a], vals[a * int(n_points):(a + 1) * int(n_points)]) for a, j in enumerate(ind)}
+
+    def profile_2d(self, covparam, param_indices=(0, 1), n=130, factor=10.0):
+        """Criterion on the n x n grid of `plot_likelihood_sigma_rho`-style profiles
+        (gpmp/modeldiagnosis/plotting.py:260-327): parameter i is swept geometrically by `factor` around its
+        value in natural units (sigma = exp(theta_0 / 2) for index 0, rho = exp(-theta_i) otherwise).
+        Returns (p1[n], p2[n], values[n, n]) with values[i, j] at (p1[j], p2[i]) like the reference's meshgrid;
+        the n * n evaluations are one batched sweep."""
+        cov0 = np.asarray(covparam, dtype=np.float64).reshape(-1)
+        i1, i2 = param_indices
+
+        def natural(i):
+            return np.exp(cov0[i] / 2.0) if i == 0 else np.exp(-cov0[i])
+
+        def to_log(i, mesh):
+            return np.log(mesh ** 2) if i == 0 else np.log(1.0 / mesh)
+
+        lf = np.log10(float(factor))
+        p1 = np.logspace(np.log10(natural(i1)) - lf, np.log10(natural(i1)) + lf, int(n))
+        p2 = np.logspace(np.log10(natural(i2)) - lf, np.log10(natural(i2)) + lf, int(n))
+        m1, m2 = np.meshgrid(p1, p2)
+        th = np.tile(cov0, (m1.size, 1))
+        th[:, i1] = to_log(i1, m1).reshape(-1)
+        th[:, i2] = to_log(i2, m2).reshape(-1)
+        vals = np.nan_to_num(self(th)).reshape(m1.shape)
+        return p1, p2, vals
+
+
 class MiniBatchCriterion:
     """Selection criterion summed over mini-batches, all equal-size batches in ONE batched launch sequence.
 

@@ -509,6 +509,29 @@ def test_minibatch_criterion(gp, case):
         gp.batched.MiniBatchCriterion(m, loader, p).gradient(th)
 
 
+def test_batched_grid_clients(gp):
+    """Cross-sections and 2-D profiles of the criterion (modeldiagnosis/plotting.py:185-231, 300-327) through
+    the batched sweep: same grids and the same values as the reference's per-point loop over the scalar path."""
+    x, z, _ = cases.data(200, 2, 70)
+    th = cases.theta(2, 70)
+    m = _model(gp, "const", 2, False, th)
+    crit = gp.batched.BatchedCriterion(m, x, z, 2)
+    f = lambda t: m.negative_log_restricted_likelihood(t, x, z).item()
+    cs = crit.cross_sections(th, n_points=7, delta=0.5)   # (a narrow box keeps K well conditioned)
+    assert sorted(cs) == [0, 1, 2]
+    for j, (grid, vals) in cs.items():
+        assert np.allclose(grid, np.linspace(th[j] - 0.5, th[j] + 0.5, 7))
+        for g, v in zip(grid[::3], vals[::3]):
+            t = th.copy(); t[j] = g
+            assert relerr(v, f(t)) <= 1e-9
+    cs = crit.cross_sections(th, ind=[2], n_points=4, param_box=np.array([[0.0], [1.0]]))
+    assert list(cs) == [2] and np.allclose(cs[2][0], np.linspace(0.0, 1.0, 4))
+    p1, p2, vals = crit.profile_2d(th, (0, 1), n=5, factor=1.5)
+    assert vals.shape == (5, 5) and np.isclose(p1[2], np.exp(th[0] / 2)) and np.isclose(p2[2], np.exp(-th[1]))
+    t = th.copy(); t[0] = np.log(p1[4] ** 2); t[1] = np.log(1.0 / p2[1])
+    assert relerr(vals[1, 4], f(t)) <= 1e-9
+
+
 def _fisher_cases():
     from oracle.make_golden_fisher import FISHER_CASES
     return FISHER_CASES
