@@ -133,6 +133,133 @@ __device__ __forceinline__ void syrk32_rows(int i8_lo, int i8_hi, int wid, int n
     }
 }
 
+// ---- factorisation of one 32x32 diagonal block of the tile: two cooperating warps ----------------------------
+// The block (origin D, leading dimension ld, in shared memory) is walked in four 8-column sub-blocks.  The PIVOT
+// warp owns the serial chain: one lane factors the 8x8 block in registers, then the warp solves only the next
+// eight rows and updates only the next 8x8 diagonal block, and goes on.  The HELPER warp (another scheduler
+// partition) solves the remaining rows of the block and applies the rest of the rank-8 update one sub-block
+// behind, under the pivot lane's next chain.  Two named-barrier rendezvous per sub-block order the hand-overs.
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ void blk8_factor(double* D, int ld, int o, double* rinv_blk, int& bad, int base) {
+    // 8x8 diagonal block: the pivot chain, entirely in registers (one lane)
+    double m[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) m[i][j] = D[(o + i) * ld + o + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double piv = m[j][j];
+        if (!(piv > 0.0) && bad == 0) bad = base + o + j + 1;
+        const double ri = fast_rsqrt(piv);
+        m[j][j] = piv * ri;
+        rinv_blk[o + j] = ri;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) m[i][j] *= ri;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+            for (int k = j + 1; k <= i; ++k) m[i][k] = fma(-m[i][j], m[k][j], m[i][k]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) D[(o + i) * ld + o + j] = m[i][j];
+}
+
+// one row of the block below the 8x8: x = p L8^-T
+__device__ __forceinline__ void blk8_solve_row(double* D, int ld, int o, const double* rinv_blk, int row) {
+    double xr[8];
+    double* myrow = D + row * ld;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) xr[t] = myrow[o + t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        xr[t] *= rinv_blk[o + t];
+#pragma unroll
+        for (int u = t + 1; u < 8; ++u) xr[u] = fma(-xr[t], D[(o + u) * ld + o + t], xr[u]);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) myrow[o + t] = xr[t];
+}
+
+// rank-8 update of the lower 8x8 tiles of the remainder (origin o + 8): FIRST = only tile (0,0) (the next
+// diagonal block), otherwise every tile of the tile rows >= 1.  All fragments first, then the independent DMMAs,
+// then the read-modify-writes.
+template <bool FIRST>
+__device__ __forceinline__ void blk8_update(double* D, int ld, int o) {
+    const int lane = threadIdx.x & 31;
+    const double* Px = D + (o + 8) * ld + o;
+    double* Cx = D + (o + 8) * ld + o + 8;
+    const int m8 = (24 - o) / 8;
+    const int gq = lane >> 2, kk = lane & 3;
+    double f0[3], f1[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const bool on = FIRST ? t == 0 : t < m8;
+        f0[t] = on ? Px[(t * 8 + gq) * ld + kk] : 0.0;
+        f1[t] = on ? Px[(t * 8 + gq) * ld + 4 + kk] : 0.0;
+    }
+    double acc[6][2];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+    for (int i8 = 0; i8 < 3; ++i8)
+#pragma unroll
+        for (int j8 = 0; j8 <= i8; ++j8) {
+            const int t = i8 * (i8 + 1) / 2 + j8;
+            const bool on = FIRST ? i8 == 0 : (i8 >= 1 && i8 < m8);  // warp-uniform
+            if (on) {
+                dmma884(acc[t][0], acc[t][1], f0[i8], f0[j8]);
+                dmma884(acc[t][0], acc[t][1], f1[i8], f1[j8]);
+            }
+        }
+#pragma unroll
+    for (int i8 = 0; i8 < 3; ++i8)
+#pragma unroll
+        for (int j8 = 0; j8 <= i8; ++j8) {
+            const int t = i8 * (i8 + 1) / 2 + j8;
+            const bool on = FIRST ? i8 == 0 : (i8 >= 1 && i8 < m8);
+            if (on) {
+                const int i = i8 * 8 + gq, j = j8 * 8 + 2 * kk;
+                if (j <= i) Cx[i * ld + j] -= acc[t][0];
+                if (j + 1 <= i) Cx[i * ld + j + 1] -= acc[t][1];
+            }
+        }
+}
+
+// PIVOT = true: the chain warp; false: the helper warp.  Both must be called by all 32 lanes of their warp.
+template <bool PIVOT>
+__device__ __forceinline__ void diag32_factor(double* D, int ld, double* rinv_blk, int c0, int& bad) {
+    const int lane = threadIdx.x & 31;
+    if (PIVOT) {
+        for (int sb = 0; sb < 4; ++sb) {
+            const int o = sb * 8;
+            if (lane == 0) blk8_factor(D, ld, o, rinv_blk, bad, c0);
+            __syncwarp();
+            if (sb < 3) {
+                pair_sync(1);  // the helper has finished the previous sub-block's rows and tiles
+                if (lane >= o + 8 && lane < o + 16) blk8_solve_row(D, ld, o, rinv_blk, lane);
+                __syncwarp();
+                blk8_update<true>(D, ld, o);
+                __syncwarp();
+                pair_sync(2);  // rows o+8..o+15 are solved: the helper may take the rest
+            }
+        }
+    } else {
+        for (int sb = 0; sb < 3; ++sb) {
+            const int o = sb * 8;
+            pair_sync(1);
+            pair_sync(2);
+            if (lane >= o + 16) blk8_solve_row(D, ld, o, rinv_blk, lane);
+            __syncwarp();
+            if (o < 16) blk8_update<false>(D, ld, o);
+            __syncwarp();
+        }
+    }
+}
+
 // Factor one 128x128 diagonal tile (lower) and invert the factor.  One CTA per tile.
 //
 // The tile lives in shared memory for the whole kernel:  S lower = L,  S strict upper = T^T
@@ -205,107 +332,19 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
     for (int jb = 0; jb < (a.mode == POTF2_INVERT ? 0 : 4); ++jb) {
         const int c0 = jb * 32;
         POTF2_STAMP(2 + 3 * jb);
-        if (warp != 0) {
-            // look-ahead: while warp 0 factors this diagonal block, the other warps finish the previous panel's
-            // trailing update (everything but this diagonal block, which was updated first)
-            if (jb > 0) {
-                const double* P = S + c0 * PLD + c0 - 32;
-                double* C = S + c0 * PLD + c0;
-                // (warps of warp 0's scheduler partition stay out: the pivot chain's DFMAs would queue behind
-                // their DMMAs in the shared FP64 pipe)
-                if (warp & 3)
-                    syrk32_rows(4, (PT - c0) / 8, warp - 1 - (warp >> 2), nwarps - nwarps / 4,
-                                [&](int r) { return P + r * PLD; }, [&](int r) { return C + r * PLD; });
-            }
-        } else {
-            double* D = S + c0 * PLD + c0;
-            for (int sb = 0; sb < 4; ++sb) {
-                const int o = sb * 8;
-                if (lane == 0) {
-                    // 8x8 diagonal block: the pivot chain, entirely in registers
-                    double m[8][8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int j = 0; j <= i; ++j) m[i][j] = D[(o + i) * PLD + o + j];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const double piv = m[j][j];
-                        if (!(piv > 0.0) && bad == 0) bad = c0 + o + j + 1;
-                        const double ri = fast_rsqrt(piv);
-                        m[j][j] = piv * ri;
-                        rinv[c0 + o + j] = ri;
-#pragma unroll
-                        for (int i = j + 1; i < 8; ++i) m[i][j] *= ri;
-#pragma unroll
-                        for (int i = j + 1; i < 8; ++i)
-#pragma unroll
-                            for (int k = j + 1; k <= i; ++k) m[i][k] = fma(-m[i][j], m[k][j], m[i][k]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int j = 0; j <= i; ++j) D[(o + i) * PLD + o + j] = m[i][j];
-                }
-                __syncwarp();
-                if (lane >= o + 8) {
-                    // rows of the block below the 8x8: x = p L8^-T, one row per lane
-                    double xr[8];
-                    double* myrow = D + lane * PLD;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) xr[t] = myrow[o + t];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        xr[t] *= rinv[c0 + o + t];
-#pragma unroll
-                        for (int u = t + 1; u < 8; ++u) xr[u] = fma(-xr[t], D[(o + u) * PLD + o + t], xr[u]);
-                    }
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) myrow[o + t] = xr[t];
-                }
-                __syncwarp();
-                if (o < 24) {
-                    // rank-8 update of the rest of the block (lower 8x8 tiles, at most 3 x 3) on the tensor
-                    // pipe: all fragments first (3 row strips serve both operands), then the independent
-                    // DMMAs, then the read-modify-writes -- one latency each instead of one per tile
-                    const double* Px = D + (o + 8) * PLD + o;
-                    double* Cx = D + (o + 8) * PLD + o + 8;
-                    const int m8 = (24 - o) / 8;
-                    const int gq = lane >> 2, kk = lane & 3;
-                    double f0[3], f1[3];
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const bool on = t < m8;
-                        f0[t] = on ? Px[(t * 8 + gq) * PLD + kk] : 0.0;
-                        f1[t] = on ? Px[(t * 8 + gq) * PLD + 4 + kk] : 0.0;
-                    }
-                    double acc[6][2];
-#pragma unroll
-                    for (int t = 0; t < 6; ++t) acc[t][0] = acc[t][1] = 0.0;
-#pragma unroll
-                    for (int i8 = 0; i8 < 3; ++i8)
-#pragma unroll
-                        for (int j8 = 0; j8 <= i8; ++j8) {
-                            const int t = i8 * (i8 + 1) / 2 + j8;
-                            if (i8 < m8) {  // warp-uniform
-                                dmma884(acc[t][0], acc[t][1], f0[i8], f0[j8]);
-                                dmma884(acc[t][0], acc[t][1], f1[i8], f1[j8]);
-                            }
-                        }
-#pragma unroll
-                    for (int i8 = 0; i8 < 3; ++i8)
-#pragma unroll
-                        for (int j8 = 0; j8 <= i8; ++j8) {
-                            const int t = i8 * (i8 + 1) / 2 + j8;
-                            if (i8 < m8) {
-                                const int i = i8 * 8 + gq, j = j8 * 8 + 2 * kk;
-                                if (j <= i) Cx[i * PLD + j] -= acc[t][0];
-                                if (j + 1 <= i) Cx[i * PLD + j + 1] -= acc[t][1];
-                            }
-                        }
-                }
-                __syncwarp();
-            }
+        if (warp == 0) {
+            diag32_factor<true>(S + c0 * PLD + c0, PLD, rinv + c0, c0, bad);
+        } else if (warp == 1) {
+            diag32_factor<false>(S + c0 * PLD + c0, PLD, rinv + c0, c0, bad);
+        } else if (jb > 0 && (warp & 3)) {
+            // look-ahead: while warps 0 and 1 factor this diagonal block, the other warps finish the previous
+            // panel's trailing update (everything but this diagonal block, which was updated first).  Warps of
+            // the pivot warp's scheduler partition stay out: its DFMA chain would queue behind their DMMAs in
+            // the shared FP64 pipe.
+            const double* P = S + c0 * PLD + c0 - 32;
+            double* C = S + c0 * PLD + c0;
+            syrk32_rows(4, (PT - c0) / 8, warp - 2 - (warp >> 2), nwarps - nwarps / 4 - 1,
+                        [&](int r) { return P + r * PLD; }, [&](int r) { return C + r * PLD; });
         }
         __syncthreads();
         POTF2_STAMP(3 + 3 * jb);
@@ -556,103 +595,16 @@ __global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2
     for (int jb = 0; jb < 4; ++jb) {
         const int c0 = jb * 32, ldd = ts_ld(jb);
         double* D = S + pk(c0, c0);  // diagonal block: rows share the leading dimension ldd
-        if (warp != 0) {
+        if (warp == 0) {
+            diag32_factor<true>(D, ldd, rinv + c0, c0, bad);
+        } else if (warp == 1) {
+            diag32_factor<false>(D, ldd, rinv + c0, c0, bad);
+        } else if (jb > 0 && (warp & 3)) {
             // look-ahead: the other warps finish the previous panel's trailing update (everything but this
-            // diagonal block, updated first) while warp 0 walks the pivot chain
-            if (jb > 0) {
-                // (warp 4 shares warp 0's scheduler partition and FP64 pipe: it stays out)
-                if (warp & 3)
-                    syrk32_rows(4, (PT - c0) / 8, warp - 1 - (warp >> 2), nwarps - nwarps / 4,
-                                [&](int r) { return S + pk(c0 + r, c0 - 32); },
-                                [&](int r) { return S + pk(c0 + r, c0); });
-            }
-        } else {
-            for (int sb = 0; sb < 4; ++sb) {
-                const int o = sb * 8;
-                if (lane == 0) {
-                    // 8x8 diagonal block: the pivot chain, entirely in registers
-                    double m[8][8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int j = 0; j <= i; ++j) m[i][j] = D[(o + i) * ldd + o + j];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const double piv = m[j][j];
-                        if (!(piv > 0.0) && bad == 0) bad = c0 + o + j + 1;
-                        const double ri = fast_rsqrt(piv);
-                        m[j][j] = piv * ri;
-                        rinv[c0 + o + j] = ri;
-#pragma unroll
-                        for (int i = j + 1; i < 8; ++i) m[i][j] *= ri;
-#pragma unroll
-                        for (int i = j + 1; i < 8; ++i)
-#pragma unroll
-                            for (int k = j + 1; k <= i; ++k) m[i][k] = fma(-m[i][j], m[k][j], m[i][k]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int j = 0; j <= i; ++j) D[(o + i) * ldd + o + j] = m[i][j];
-                }
-                __syncwarp();
-                if (lane >= o + 8) {
-                    // rows of the block below the 8x8: x = p L8^-T, one row per lane
-                    double xr[8];
-                    double* myrow = D + lane * ldd;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) xr[t] = myrow[o + t];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        xr[t] *= rinv[c0 + o + t];
-#pragma unroll
-                        for (int u = t + 1; u < 8; ++u) xr[u] = fma(-xr[t], D[(o + u) * ldd + o + t], xr[u]);
-                    }
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) myrow[o + t] = xr[t];
-                }
-                __syncwarp();
-                if (o < 24) {
-                    // rank-8 update of the rest of the block (lower 8x8 tiles, at most 3 x 3) on the tensor
-                    // pipe: all fragments first, then the independent DMMAs, then the read-modify-writes
-                    const double* Px = D + (o + 8) * ldd + o;
-                    double* Cx = D + (o + 8) * ldd + o + 8;
-                    const int m8 = (24 - o) / 8;
-                    const int gq = lane >> 2, kk = lane & 3;
-                    double f0[3], f1[3];
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const bool on = t < m8;
-                        f0[t] = on ? Px[(t * 8 + gq) * ldd + kk] : 0.0;
-                        f1[t] = on ? Px[(t * 8 + gq) * ldd + 4 + kk] : 0.0;
-                    }
-                    double acc[6][2];
-#pragma unroll
-                    for (int t = 0; t < 6; ++t) acc[t][0] = acc[t][1] = 0.0;
-#pragma unroll
-                    for (int i8 = 0; i8 < 3; ++i8)
-#pragma unroll
-                        for (int j8 = 0; j8 <= i8; ++j8) {
-                            const int t = i8 * (i8 + 1) / 2 + j8;
-                            if (i8 < m8) {  // warp-uniform
-                                dmma884(acc[t][0], acc[t][1], f0[i8], f0[j8]);
-                                dmma884(acc[t][0], acc[t][1], f1[i8], f1[j8]);
-                            }
-                        }
-#pragma unroll
-                    for (int i8 = 0; i8 < 3; ++i8)
-#pragma unroll
-                        for (int j8 = 0; j8 <= i8; ++j8) {
-                            const int t = i8 * (i8 + 1) / 2 + j8;
-                            if (i8 < m8) {
-                                const int i = i8 * 8 + gq, j = j8 * 8 + 2 * kk;
-                                if (j <= i) Cx[i * ldd + j] -= acc[t][0];
-                                if (j + 1 <= i) Cx[i * ldd + j + 1] -= acc[t][1];
-                            }
-                        }
-                }
-                __syncwarp();
-            }
+            // diagonal block, updated first) while warps 0 and 1 walk the pivot chain (warp 4 shares warp 0's
+            // scheduler partition and FP64 pipe: it stays out)
+            syrk32_rows(4, (PT - c0) / 8, warp - 2 - (warp >> 2), nwarps - nwarps / 4 - 1,
+                        [&](int r) { return S + pk(c0 + r, c0 - 32); }, [&](int r) { return S + pk(c0 + r, c0); });
         }
         __syncthreads();
         const int rb = c0 + 32;       // first row below the diagonal block
