@@ -140,3 +140,70 @@ def test_autoselect_parameters_maps_linear_algebra_failures_to_inf():
 
     with pytest.raises(KeyError):
         selection.autoselect_parameters(np.array([0.0]), broken, lambda p: np.zeros(1))
+
+
+# ---- mini-batch criterion: host logic (grouping by batch size, reductions, cycling) without a device ----------
+def test_minibatch_criterion_host_logic_with_oracle_ops(monkeypatch):
+    """MiniBatchCriterion stacks equal-size batches into one batched call and sends the ragged batch through the
+    scalar path; here both device entry points are replaced by the CPU oracle, so the grouping, the weighting
+    by batch size, both reductions and `batches_per_eval` are checked on CPU against the reference's own
+    BatchDifferentiableSelectionCriterion (golden vectors)."""
+    from gpmp_b200 import batched, ops
+    from oracle import cases, gp_torch as otorch
+    from oracle.make_golden_minibatch import MINIBATCH_CASES
+
+    calls = {"batched": 0, "entries": 0, "scalar": 0}
+
+    def fake_batched(theta, x, z, P, p, noise=False, max_bytes=None, work=None):
+        calls["batched"] += 1
+        calls["entries"] += theta.shape[0]
+        vals, grads = [], []
+        for b in range(theta.shape[0]):
+            v, g = otorch.reml_value_and_grad(x[b], z[b], P, p, theta[b], noise)
+            vals.append(v)
+            grads.append(g)
+        return (torch.tensor(vals, dtype=torch.float64), torch.tensor(np.array(grads), dtype=torch.float64),
+                torch.zeros(theta.shape[0], dtype=torch.int32))
+
+    def fake_scalar(param, z, x, P, p, noise=False):
+        calls["scalar"] += 1
+        if P is None:
+            return otorch.nll_zero_mean(x, z, p, param, noise)
+        return otorch.reml(x, z, P, p, param, noise)
+
+    monkeypatch.setattr(ops, "to_device", lambda a, requires_contiguous=True: torch.as_tensor(a, dtype=torch.float64))
+    monkeypatch.setattr(ops, "criterion_batched_grad", fake_batched)
+    monkeypatch.setattr(ops, "criterion_batched_grad_workspace", lambda n, q, d, N, max_bytes=None: None)
+    monkeypatch.setattr(ops, "fused_likelihood", fake_scalar)
+
+    class _Model:
+        def __init__(self, kind):
+            self.mean, self.meanparam = cases.mean_fn(kind, torch), None
+            self.meantype = cases.meantype_of(kind)
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_minibatch.npz"))
+    for name, n, bs, d, p, kind, seed in MINIBATCH_CASES:
+        x, z, th = g[name + "/x"], g[name + "/z"], g[name + "/theta"]
+        loader = [(x[i:i + bs], z[i:i + bs]) for i in range(0, n, bs)]
+        nfull, ragged = n // bs, int(n % bs != 0)
+        for red in ("mean", "sum"):
+            calls.update(batched=0, entries=0, scalar=0)
+            c = batched.MiniBatchCriterion(_Model(kind), loader, p, kind="ml" if kind == "zero" else "reml",
+                                           reduction=red)
+            v = c.evaluate_pre_grad(th)
+            assert calls == {"batched": 1, "entries": nfull, "scalar": ragged}
+            assert abs(v - float(g[f"{name}/{red}/value"])) <= 1e-9 * abs(v)
+            gr = np.asarray(c.gradient(th))
+            ref = g[f"{name}/{red}/grad"]
+            assert np.linalg.norm(gr - ref) <= 1e-8 * np.linalg.norm(ref)
+        # two batches per evaluation, cycling through the loader
+        c = batched.MiniBatchCriterion(_Model(kind), loader, p, kind="ml" if kind == "zero" else "reml",
+                                       batches_per_eval=2)
+        calls.update(batched=0, entries=0, scalar=0)
+        for _ in range(len(loader)):
+            c.evaluate(th)
+        assert calls["entries"] + calls["scalar"] == 2 * len(loader)
+    with pytest.raises(ValueError):
+        batched.MiniBatchCriterion(_Model("const"), [], 2)
+    with pytest.raises(ValueError):
+        batched.MiniBatchCriterion(_Model("const"), loader, 2, reduction="median")
