@@ -171,15 +171,18 @@ class MiniBatchCriterion:
         self._work, self._wkey = None, None
 
     def _batches(self):
+        """The batches of one evaluation: the whole loader, or the next `batches_per_eval` ones (the loader is
+        restarted when it runs out, so evaluations cycle through the data)."""
         if self.bpe == 0:
-            yield from self.loader
-        else:
-            for _ in range(self.bpe):
-                try:
-                    yield next(self._batch_iter)
-                except StopIteration:
-                    self._batch_iter = iter(self.loader)
-                    yield next(self._batch_iter)
+            return list(self.loader)
+        picked = []
+        while len(picked) < self.bpe:
+            item = next(self._batch_iter, None)
+            if item is None:
+                self._batch_iter = iter(self.loader)
+                continue
+            picked.append(item)
+        return picked
 
     def _basis(self, xb):
         if self.kind != "reml":
