@@ -17,7 +17,10 @@
 // solve (they leave as B L^-T).  The NB-wide inverses of the diagonal blocks, which the triangular inverse
 // and the row solves start from, are assembled afterwards by block doubling
 // (inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1,C^-1]]).  Single large matrices run a three-stream
-// look-ahead (potrf_core); the same pieces serve the panel-partitioned multi-GPU loop (dist_*).
+// look-ahead (potrf_core) whose chain uses the factor-only tile kernel and the substitution solve
+// (trsm_tile_kernel) instead of the tile inverse; batched value-only sweeps use the packed factor-only tile
+// kernel (two tiles per SM) and one solve CTA per matrix; the same pieces serve the panel-partitioned
+// multi-GPU loop (dist_*).
 #include <vector>
 #include "internal.cuh"
 
@@ -29,7 +32,7 @@ constexpr int XLD = 68;          // smem leading dimension of the scratch (4 mod
 constexpr int POTF2_THREADS = 512;
 constexpr int POTF2_SMEM = (PT * PLD + 96 * XLD + PT) * 8;
 // Packed lower tile: block row b (32 rows) keeps its 32 (b + 1) leading columns with leading dimension
-// 32 b + 36 (= 4 mod 16: conflict-free DMMA fragment loads); 10752 doubles instead of 128 x 130.
+// 32 b + 36 (= 4 mod 16: conflict-free DMMA fragment loads); 10752 doubles instead of 128 x 132.
 constexpr int TS_LP = 10752;
 __device__ __forceinline__ int ts_ld(int b) { return 32 * b + 36; }
 __device__ __forceinline__ int ts_base(int b) { return 512 * b * (b - 1) + 1152 * b; }
