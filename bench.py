@@ -5,25 +5,33 @@
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm (oracle port of the reference)
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm: GPmp itself (oracle/_ref) on the host
 
 One step = one evaluation of Model.negative_log_restricted_likelihood and its 9-component covparam
 gradient (Matern p=2, constant mean) on x ~ U[0,1]^{8192x8}, z = sin(3 sum x) + 0.1 N(0,1), seed 1234.
 A single evaluation does not shard ("replicas only"), so at N > 1 every rank evaluates its
 own parameter vector (multi-start restarts): scaling is weak, value = N*K / max-over-ranks time.
 
-value    : device-resident inputs (x, z already in HBM); theta (9 doubles) goes in by value and the
-           scalar + gradient come back through pinned memory every step (the optimiser needs them).
-e2e      : the same K steps through the public API with HOST numpy inputs: x, z and theta are copied
-           host->device inside the timed region every step, value and gradient are read back.
-roofline : FP64 tensor (DMMA) pipe.  achieved = n^3 flop per evaluation (potrf n^3/3 + trtri n^3/3 +
-           lauum n^3/3) / step time -- a lower bound of the DMMA GEMM's rate, because its launches
-           overlap on three streams; the per-launch CUDA-event sums (second pass over the same K steps, events
-           on each launching stream) are reported per kernel class beside it.
+value     : device-resident inputs (x, z already in HBM); theta (9 doubles) goes in by value and the
+            scalar + gradient come back through pinned memory every step (the optimiser needs them).
+e2e       : the same K steps through the public API with HOST numpy inputs: x, z and theta are copied
+            host->device inside the timed region every step, value and gradient are read back.
+roofline  : FP64 tensor (DMMA) pipe.  achieved = n^3 flop per evaluation (potrf n^3/3 + trtri n^3/3 +
+            lauum n^3/3) / step time.  peak = the DMMA issue rate MEASURED in this run
+            (gpmp_measure_dmma_peak: every SM issuing DMMA.8x8x4 from registers), with cuBLAS dgemm 8192^3
+            (best of 10) and the nominal 40 TFLOP/s beside it.  per_class: CUDA-event times per kernel class
+            from a serialised pass (all look-ahead streams folded onto one stream: exclusive times) and from
+            the overlapped production schedule, with the algorithmic work of each class.
+parity    : the CPU arm evaluates the SAME theta as the last timed GPU step; value / gradient relative
+            errors are printed and the bench fails above 1e-8 (BASELINE.json tolerance).
+secondary : the paths north_star wants to SCALE, timed across the same N ranks: the 8192-particle x n=512
+            batched REML sweep (rows sharded, one all-gather) and the panel-partitioned n=32768 value + gradient
+            (--no-secondary / --no-secondary-large skip them).
 """
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import statistics
@@ -39,12 +47,12 @@ sys.path.insert(0, ROOT)
 
 N_OBS, DIM, P_MATERN, SEED = 8192, 8, 2, 1234
 METRIC = "REML logL+grad evals/s (n=8192,d=8,fp64)"
+WORKLOAD = "REML value+grad n=8192 d=8 Matern p=2 constant mean (BASELINE configs[2])"
 FP64_NOMINAL_TFLOPS = 40.0  # HGX B200 datasheet; MEASURED_PEAKS.json carries no fp64 entry
-# DRAM bytes of all DMMA launches (gemm_nt_kernel + trsm_tile_kernel) of one evaluation: dram__bytes_read.sum +
-# dram__bytes_write.sum summed over the 201 launches, ncu capture committed as
-# profiles/r01_gemm_dram_one_eval.csv (10.23 GB read + 1.29 GB written: 64x64 tiles re-read operands from L2/HBM
-# more often than 128x128 tiles did -- 5.6 GB -- and still sit at ~0.5 TB/s, far below the HBM roofline)
-GEMM_DRAM_BYTES_PER_STEP = 10.227e9 + 1.286e9
+TOL_PARITY = 1e-8
+# ncu capture of the DRAM traffic of every DMMA launch of one evaluation (dram__bytes_read/write.sum per launch);
+# summed at run time so the line always quotes the committed capture it names
+TRAFFIC_CSVS = ["profiles/r02_gemm_dram_one_eval.csv", "profiles/r01_gemm_dram_one_eval.csv"]
 
 
 def headline_inputs(n=N_OBS, d=DIM, seed=SEED):
@@ -62,7 +70,7 @@ def thetas_for(th0, count, rank):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -114,45 +122,37 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_eval_seconds(n, d, threads_note=True):
-    """One REML value + gradient on the host with the oracle port of the reference's torch backend
-    (autograd through every op: gpmp/num/torch_backend.py:516-533 over core/likelihood.py:92-129)."""
-    from oracle import gp_torch as ot
-
-    x, z, th0 = headline_inputs(n, d)
-    P = np.ones((n, 1))
-    t0 = time.perf_counter()
-    v, g = ot.reml_value_and_grad(x, z, P, P_MATERN, th0)
-    return time.perf_counter() - t0, float(v)
-
-
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the reference is pure Python and
-    cannot travel to the GPU box), all host threads, one bounded sample per step."""
-    import torch
-
+    """--impl reference: GPmp's own CPU implementation of the step (oracle/_ref: the unmodified package, torch
+    backend, gnp.value_and_grad of Model.negative_log_restricted_likelihood) on all host cores, at the FULL
+    n=8192 workload.  One evaluation is ~10 s of host time, so at most 3 evaluations are timed (and at most one
+    warmed up) whatever --steps / --warmup ask for; the line says so.  Under torchrun rank 0 alone runs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # full size when the run stays within a few minutes (one evaluation is ~7-25 s of host time),
-    # otherwise n = 4096 scaled by n^3 (the O(n^2 d) terms make the scaled figure slightly pessimistic)
-    n_s = args.ref_n if args.ref_n else (N_OBS if (args.steps + args.warmup) <= 8 else 4096)
-    scale = (N_OBS / n_s) ** 3
-    for _ in range(args.warmup):
-        cpu_eval_seconds(n_s, DIM)
-    ts = [cpu_eval_seconds(n_s, DIM)[0] for _ in range(args.steps)]
+    from oracle import ref_eval
+
+    cores = ref_eval.use_all_host_threads()
+    n_s = args.ref_n if args.ref_n else N_OBS
+    x, z, th0 = headline_inputs(n_s, DIM)
+    ev = ref_eval.RemlEvaluator(x, z, P_MATERN)
+    timed = max(1, min(args.steps, 3))
+    warm = min(args.warmup, 1)
+    ths = thetas_for(th0, warm + timed, 0)
+    for th in ths[:warm]:
+        ev(th)
+    ts = [ev(th)[2] for th in ths[warm:]]
     total = sum(ts)
-    value = args.steps / (total * scale)
-    sample = (f"each step = 1 REML value+grad at n={n_s},d={DIM} (torch-CPU autograd, oracle port)"
-              + ("" if n_s == N_OBS else f", time scaled by (8192/{n_s})^3={scale:.0f} to the n=8192 workload"))
-    cores = torch.get_num_threads()
+    value = timed / total
+    sample = (f"{timed} full-size evaluations timed (of --steps {args.steps}; {warm} warm-up): each = 1 REML value + "
+              f"gradient at n={n_s}, d={DIM}, by {ev.describe()}, {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total * scale / args.steps,
+        "steps": timed, "warmup": warm, "steps_requested": args.steps, "ms_per_step": 1e3 * total / timed,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "REML value+grad n=8192 d=8 Matern p=2 constant mean (configs[2])",
+        "config": {"workload": WORKLOAD if n_s == N_OBS else f"REML value+grad n={n_s} (test override)",
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": ev.kind, "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpus": os.cpu_count(),
     }
@@ -160,6 +160,128 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def measure_fp64_peaks(torch, _abi):
+    """(DMMA issue-rate TFLOP/s, cuBLAS dgemm 8192^3 TFLOP/s), both best of 10 with CUDA events."""
+    import ctypes as C
+
+    lib = _abi.lib()
+    sink = torch.zeros(148 * 8 * 512, dtype=torch.float64, device="cuda")
+    flops = C.c_double()
+    best = 0.0
+    for it in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _abi.check(lib.gpmp_measure_dmma_peak(148 * 8, 20000, _abi.ptr(sink), C.byref(flops), _abi.stream_ptr()),
+                   "gpmp_measure_dmma_peak")
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    A = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    B = torch.empty_like(A)
+    cub = 0.0
+    for it in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(A, A, out=B)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            cub = max(cub, 2 * 8192**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del A, B
+    return best, cub
+
+
+def committed_traffic():
+    """DRAM bytes per evaluation over all DMMA launches, summed from the committed ncu capture (or None)."""
+    for rel in TRAFFIC_CSVS:
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        total, hit = 0.0, False
+        with open(path, newline="") as f:
+            rows = [r for r in csv.reader(f) if r]
+        header = next((r for r in rows if "Metric Name" in r and "Metric Value" in r), None)
+        if header is None:
+            continue
+        iname, ival, iunit = header.index("Metric Name"), header.index("Metric Value"), header.index("Metric Unit")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows:
+            if len(r) <= max(iname, ival, iunit) or not r[iname].startswith("dram__bytes_"):
+                continue
+            try:
+                total += float(r[ival].replace(",", "")) * scale.get(r[iunit], 1.0)
+                hit = True
+            except ValueError:
+                pass
+        if hit:
+            return total, rel
+    return None, None
+
+
+def secondary_paths(args, torch, dist, gp, world, rank, peak_tf):
+    """The sharded paths of SURVEY.md 8(e), timed on the same ranks with the same barrier / max-over-ranks rule."""
+    out = {}
+    group = dist.group.WORLD if world > 1 else None
+
+    def timed(fn, reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / reps
+
+    # --- BASELINE configs[3]: 8192 particles x (n=512, d=4), REML values, rows sharded over the ranks
+    n, d, N = 512, 4, 8192
+    rng = np.random.default_rng(4321)
+    x = rng.uniform(size=(n, d))
+    z = np.sin(3.0 * x.sum(axis=1)) + 0.1 * rng.standard_normal(n)
+    th_hat = np.concatenate(([0.0], np.full(d, -np.log(0.5))))
+    TH = th_hat + rng.uniform(-2.0, 2.0, size=(N, d + 1))
+    model = gp.core.Model(lambda x_, mp: gp.num.ones((x_.shape[0], 1)),
+                          lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, P_MATERN, cp, pairwise))
+    crit = gp.batched.BatchedCriterion(model, x, z, P_MATERN, kind="reml", group=group)
+    vals = crit(TH)
+    crit(TH)
+    ms = timed(lambda: crit(TH), 5)
+    flops = N * float(n) ** 3 / 3.0
+    tf = flops / (ms * 1e-3) / 1e12
+    out["smc_sweep"] = {
+        "workload": "8192 particles x REML value at n=512, d=4 (BASELINE configs[3]); host theta in, host values out",
+        "ms_per_sweep": ms, "sweeps_per_s": 1e3 / ms, "particle_evals_per_s": N * 1e3 / ms,
+        "tflops_aggregate": tf, "frac_of_peak_per_gpu": tf / world / peak_tf,
+        "algorithmic_flops_per_sweep": flops, "finite_values": int(np.isfinite(vals).sum()),
+        "sharding": f"theta rows block-partitioned over {world} rank(s); one all-gather of N values per sweep",
+    }
+    if not args.no_secondary_large:
+        # --- BASELINE configs[4]: one n=32768, d=10 REML value + gradient, factorisation / inverse partitioned
+        n2, d2 = 32768, 10
+        x2, z2, _ = headline_inputs(n2, d2, seed=99)
+        th2 = np.concatenate(([0.0], np.full(d2, -np.log(0.7))))
+        m2 = gp.core.Model(lambda x_, mp: gp.num.ones((x_.shape[0], 1)),
+                           lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, P_MATERN, cp, pairwise))
+        xd, zd = gp.num.asarray(x2), gp.num.asarray(z2)
+        gp.dist.reml_value_and_grad_distributed(m2, th2, xd, zd, group)
+        ms2 = timed(lambda: gp.dist.reml_value_and_grad_distributed(m2, th2, xd, zd, group), 2)
+        tf2 = float(n2) ** 3 / (ms2 * 1e-3) / 1e12
+        out["partitioned_reml_n32768"] = {
+            "workload": "one REML value+grad at n=32768, d=10 (BASELINE configs[4]); panel-partitioned over the ranks",
+            "ms_per_eval": ms2, "tflops_aggregate": tf2, "frac_of_peak_per_gpu": tf2 / world / peak_tf,
+            "algorithmic_flops": float(n2) ** 3,
+        }
+        del xd, zd
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -231,89 +353,110 @@ def run_gpu(args):
     h2d = 8 * (x.size + z.size + th0.size)
     d2h = 8 * 8 + 8 * th0.size  # 64-byte value/info record + gradient
 
-    # roofline pass: per-launch CUDA events on the launching stream over the same K steps
-    _abi.prof_enable(True)
-    torch.cuda.synchronize()
-    for th in ths[args.warmup:]:
-        step(th, xd, zd)
-    torch.cuda.synchronize()
+    # roofline passes over (up to 5 of) the same steps with per-launch CUDA events: overlapped production
+    # schedule (times overlap across the look-ahead streams) and serialised (exclusive times)
+    names = ["matern_cov", "dmma_gemm", "potf2", "dk_contract", "small", "batched"]
+    prof_steps = ths[args.warmup:][: min(5, args.steps)]
     prof = {}
-    for cls, name in enumerate(["matern_cov", "dmma_gemm", "potf2", "dk_contract", "small", "batched"]):
-        pms, cnt, work = _abi.prof_read(cls)
-        prof[name] = {"ms_per_step": pms / args.steps, "launches_per_step": cnt / args.steps}
-    _abi.prof_enable(False)
+    for mode, key in ((2, "serialised"), (1, "overlapped")):
+        _abi.prof_enable(mode)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for th in prof_steps:
+            step(th, xd, zd)
+        e1.record()
+        torch.cuda.synchronize()
+        per = {}
+        for cls, name in enumerate(names):
+            pms, cnt, work = _abi.prof_read(cls)
+            k = len(prof_steps)
+            per[name] = {"ms_per_step": pms / k, "launches_per_step": cnt / k, "work_per_step": work / k}
+            if name in ("dmma_gemm", "potf2") and pms > 0:
+                per[name]["tflops"] = work / (pms * 1e-3) / 1e12
+            if name in ("matern_cov", "dk_contract") and pms > 0:
+                per[name]["gbytes_per_s"] = work / (pms * 1e-3) / 1e9
+        _abi.prof_enable(0)
+        prof[key] = {"step_ms_with_events": e0.elapsed_time(e1) / len(prof_steps), "per_class": per}
     flops = float(N_OBS) ** 3
-    gemm_ms = prof["dmma_gemm"]["ms_per_step"]
-    gemm_event_sum_tflops = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    # The DMMA GEMM launches of one step overlap on three streams (bulk / chain / helper), so their event times
-    # sum to MORE than the step; n^3 / step time is therefore a lower bound of the kernel's rate and is what is
-    # reported as `achieved` (the event-sum figure is kept beside it).
     achieved = flops / (ms * 1e-3 / args.steps) / 1e12
+
+    dmma_peak, cublas_tf = measure_fp64_peaks(torch, _abi)
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_paths(args, torch, dist, gp, world, rank, dmma_peak)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # cuBLAS dgemm on this GPU, for context next to the nominal peak
-    A = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
-    for _ in range(2):
-        A @ A
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        A @ A
-    e1.record()
-    torch.cuda.synchronize()
-    cublas_tf = 5 * 2 * 4096**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
-    del A
-
+    traffic, traffic_src = committed_traffic()
+    ser = prof["serialised"]["per_class"]
     roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
-        "frac": achieved / FP64_NOMINAL_TFLOPS, "traffic": GEMM_DRAM_BYTES_PER_STEP,
-        "traffic_note": "bytes per step over all launches of the kernel (profiles/r01_gemm_dram_one_eval.csv)",
+        "bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
+        "frac": achieved / dmma_peak, "traffic": traffic,
+        "traffic_note": (f"dram__bytes_read+write summed over all DMMA launches of one evaluation ({traffic_src})"
+                         if traffic_src else "no committed ncu capture found"),
         "kernel": "gpmp::gemm_nt_kernel (FP64 DMMA.8x8x4)",
-        "peak_source": "nominal HGX B200 FP64 (MEASURED_PEAKS.json has no fp64 entry); cuBLAS dgemm 4096^3 "
-                       f"measured in this run: {cublas_tf:.1f} TFLOP/s",
+        "peak_source": "FP64 tensor pipe issue rate measured in this run (gpmp_measure_dmma_peak: 148x8 CTAs x 16 warps "
+                       "x 8 independent DMMA.8x8x4 chains from registers, best of 10); MEASURED_PEAKS.json has no fp64 "
+                       "entry",
+        "peak_cublas_dgemm_8192": cublas_tf, "peak_nominal": FP64_NOMINAL_TFLOPS,
+        "frac_of_cublas_dgemm": achieved / cublas_tf, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
         "algorithmic_flops_per_step": flops,
-        "achieved_basis": "n^3 flop / step time: lower bound of the kernel's rate (its launches overlap on three "
-                          "streams, so per-launch CUDA-event times sum to more than the step)",
-        "gemm_event_sum_tflops": gemm_event_sum_tflops,
-        "per_class": prof,
+        "achieved_basis": "n^3 flop / step time (whole step: K build, factorisation, inverse, contraction, readbacks)",
+        "kernel_rate_exclusive_tflops": ser["dmma_gemm"].get("tflops"),
+        "kernel_share_of_serialised_step": (ser["dmma_gemm"]["ms_per_step"]
+                                            / max(1e-9, sum(c["ms_per_step"] for c in ser.values()))),
+        "passes": prof,
     }
 
-    cpu = None
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
-        t_probe, _ = cpu_eval_seconds(2048, DIM)
-        est = t_probe * 64
-        n_s = N_OBS if est <= 45.0 else 4096
-        t_s, _ = cpu_eval_seconds(n_s, DIM)
-        scale = (N_OBS / n_s) ** 3
-        cpu = {"value": 1.0 / (t_s * scale), "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 REML value+grad at n={n_s},d={DIM} with the oracle port (torch-CPU autograd), "
-                         + ("measured at full size" if n_s == N_OBS else f"scaled by (8192/{n_s})^3"),
+        from oracle import ref_eval
+
+        cores = ref_eval.use_all_host_threads()
+        ev = ref_eval.RemlEvaluator(x, z, P_MATERN)
+        th_last = ths[-1]
+        if args.cpu_warm:
+            ev(th_last)
+        v_ref, g_ref, t_s = ev(th_last)
+        cpu = {"value": 1.0 / t_s, "unit": "evals/s", "cores": cores, "kind": ev.kind,
+               "sample": f"1 full-size evaluation (n={N_OBS}, d={DIM}) at the theta of the last timed GPU step, by "
+                         f"{ev.describe()}, {cores} threads, {t_s:.1f} s",
                "host_cpus": os.cpu_count()}
+        v_gpu, g_gpu = last
+        parity = {"theta": "last timed step", "value_gpu": v_gpu, "value_cpu": v_ref,
+                  "value_rel": abs(v_gpu - v_ref) / abs(v_ref),
+                  "grad_rel": float(np.max(np.abs(g_gpu - g_ref)) / np.max(np.abs(g_ref))),
+                  "tolerance": TOL_PARITY}
+        parity["ok"] = bool(parity["value_rel"] <= TOL_PARITY and parity["grad_rel"] <= TOL_PARITY)
 
     line = {
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "REML value+grad n=8192 d=8 Matern p=2 constant mean (BASELINE configs[2])",
+        "config": {"workload": WORKLOAD,
                    "parallelism": f"replicas x{world} (one evaluation does not shard; independent restarts)",
                    "l2": "working set per step ~2.2 GB (L, T, T^T, K^-1) >> 126 MB L2; no flush needed",
-                   "roofline_pass": "second pass over the same steps with per-launch CUDA events"},
+                   "roofline_pass": "two extra passes over the same steps with per-launch CUDA events"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
+        "secondary": secondary,
         "last_value": last[0],
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        print(f"bench: parity check failed: {parity}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -323,6 +466,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpmp_b200", choices=["gpmp_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-warm", action="store_true", help="cpu_baseline: one untimed evaluation first")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the sharded config-4 sweep")
+    ap.add_argument("--no-secondary-large", action="store_true",
+                    help="skip the panel-partitioned n=32768 value+grad of the secondary block")
     ap.add_argument("--ref-n", type=int, default=0, help="reference arm: sample size override (tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

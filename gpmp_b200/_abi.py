@@ -58,6 +58,7 @@ SIGNATURES = {
     "gpmp_matern_cov_pairwise": (_i, [_specp, _vp, _vp, _i, _vp, _vp]),
     "gpmp_contract_workspace_bytes": (_sz, [_i, _i, _i]),
     "gpmp_matern_cov_backward": (_i, [_specp, _vp, _i, _vp, _i, _vp, _ll, _vp, _vp, _sz, _vp]),
+    "gpmp_measure_dmma_peak": (_i, [_i, _i, _vp, C.POINTER(C.c_double), _vp]),
     "gpmp_potrf_workspace_bytes": (_sz, [_i, _i]),
     "gpmp_potrf": (_i, [_vp, _i, _i, _ll, _vp, _sz, _vp, _vp]),
     "gpmp_potri": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _vp, _ll, _vp]),
@@ -160,7 +161,8 @@ def launch_count():
 
 
 def prof_enable(flag):
-    lib().gpmp_prof_enable(1 if flag else 0)
+    """0 off, 1 per-launch CUDA events, 2 the same with the look-ahead streams serialised (exclusive times)."""
+    lib().gpmp_prof_enable(int(flag))
 
 
 def prof_read(cls):

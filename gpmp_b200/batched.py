@@ -19,6 +19,13 @@ from . import dist as gdist
 from . import ops
 
 
+def _mean_values(model, x):
+    """mean(x, meanparam) on the device for gpmp_b200.core.Model (which knows whether the callable wants host
+    points) or any object with the reference Model's `mean` / `meanparam` attributes."""
+    f = getattr(model, "mean_values", None)
+    return f(x) if f is not None else ops.to_device(model.mean(x, model.meanparam))
+
+
 class BatchedCriterion:
     def __init__(self, model, xi, zi, p, kind="reml", noise=False, group=None, max_bytes=None):
         if kind not in ("reml", "ml"):
@@ -28,10 +35,10 @@ class BatchedCriterion:
         self.p, self.noise, self.kind = int(p), bool(noise), kind
         self.P = None
         if kind == "reml":
-            P = ops.to_device(model.mean(self.x, model.meanparam))
+            P = _mean_values(model, self.x)
             self.P = (P.reshape(-1, 1) if P.dim() == 1 else P).contiguous()
         elif model.meantype == "parameterized":
-            z = z - ops.to_device(model.mean(self.x, model.meanparam)).reshape(-1)
+            z = z - _mean_values(model, self.x).reshape(-1)
         self.z = z.contiguous()
         self.group = group
         self.max_bytes = max_bytes
@@ -187,7 +194,7 @@ class MiniBatchCriterion:
     def _basis(self, xb):
         if self.kind != "reml":
             return None
-        P = ops.to_device(self.model.mean(xb, self.model.meanparam))
+        P = _mean_values(self.model, xb)
         return (P.reshape(-1, 1) if P.dim() == 1 else P).contiguous()
 
     def _evaluate(self, param, want_grad):

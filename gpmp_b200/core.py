@@ -74,6 +74,15 @@ class Model:
         self.meanparam = meanparam
         self.covparam = covparam
         self.covariance = covariance
+        # True: the user's `mean` callable is written against a HOST array namespace (GPmp's own gnp when this
+        # library is bound into it, gpmp_b200/dropin.py); it then receives host copies of the points and its
+        # result is moved to the device here
+        self.host_mean = False
+
+    def mean_values(self, x, meanparam=None):
+        """mean(x, meanparam) on the device, whatever array namespace the callable is written against."""
+        xin = x.cpu() if (self.host_mean and torch.is_tensor(x) and x.device.type != "cpu") else x
+        return ops.to_device(self.mean(xin, self.meanparam if meanparam is None else meanparam))
 
     def __repr__(self):
         return "<gpmp_b200.core.Model object> " + hex(id(self))
@@ -97,8 +106,7 @@ class Model:
             return num.safe_inf()
 
     def _basis(self, x, meanparam=None):
-        P = self.mean(x, self.meanparam if meanparam is None else meanparam)
-        P = ops.to_device(P)
+        P = self.mean_values(x, meanparam)
         if P.dim() == 1:
             P = P.reshape(-1, 1)
         return P
@@ -113,7 +121,7 @@ class Model:
     def negative_log_likelihood(self, meanparam, covparam, xi, zi):
         """Zero-mean NLL of z - mean(x, meanparam) (core/likelihood.py:55-89); differentiable in both."""
         xi, zi, _ = _ensure_shapes_and_type(xi=xi, zi=zi)
-        prior_mean = ops.to_device(self.mean(xi, _as_param(meanparam))).reshape(-1)
+        prior_mean = self.mean_values(xi, _as_param(meanparam)).reshape(-1)
         v = self._criterion(covparam, xi, zi - prior_mean, None)
         return v.reshape(()) if torch.isfinite(v) else v
 
@@ -190,7 +198,7 @@ class Model:
         if self.meantype == "linear_predictor":
             P = self._basis(xi)
         elif self.meantype == "parameterized":
-            prior = ops.to_device(self.mean(xi, _as_param(self.meanparam))).reshape(-1)
+            prior = self.mean_values(xi, _as_param(self.meanparam)).reshape(-1)
             zc = zi - prior
         with torch.no_grad():
             state, out = self._fit(xi, zc, P, covparam, with_inverse=True)
@@ -216,7 +224,7 @@ class Model:
         elif self.meantype == "parameterized":
             if self.meanparam is None:
                 raise ValueError("For meantype 'parameterized', meanparam should not be None.")
-            zi_prior = ops.to_device(self.mean(xi, _as_param(self.meanparam))).reshape(-1)
+            zi_prior = self.mean_values(xi, _as_param(self.meanparam)).reshape(-1)
             zc = zi - zi_prior
         elif self.meantype != "zero":
             raise ValueError(f"Invalid meantype {self.meantype}.")
@@ -276,8 +284,8 @@ class Model:
         """Same with a parameterised prior mean (core/sample_paths.py:122-182)."""
         xi_, zi_, xt_ = _ensure_shapes_and_type(xi=xi, zi=zi, xt=xt)
         mp = _as_param(self.meanparam)
-        zc = zi_ - ops.to_device(self.mean(xi_, mp)).reshape(-1)
-        zt_prior = ops.to_device(self.mean(xt_, mp)).reshape(-1, 1)
+        zc = zi_ - self.mean_values(xi_, mp).reshape(-1)
+        zt_prior = self.mean_values(xt_, mp).reshape(-1, 1)
         return self._condition(ztsim, xi_ind, zc, xt_ind, lambda_t, zt_prior, convert_out)
 
     def _condition(self, ztsim, xi_ind, zc, xt_ind, lambda_t, zt_prior, convert_out):
@@ -338,7 +346,7 @@ class Fitted:
         Pt = model._basis(xt).contiguous() if model.meantype == "linear_predictor" else None
         prior = None
         if model.meantype == "parameterized":
-            prior = ops.to_device(model.mean(xt, _as_param(model.meanparam))).reshape(-1)
+            prior = model.mean_values(xt, _as_param(model.meanparam)).reshape(-1)
         return Pt, prior
 
     def predict(self, xt, return_lambdas=False, zero_neg_variances=True, convert_out=True):

@@ -1,5 +1,6 @@
 // The C-ABI of libgpmp_b200 (include/gpmp_b200.h): argument checks, workspace layouts and the launch
 // sequences.  Nothing here allocates, synchronises or throws; every call only enqueues on `stream`.
+#include <mutex>
 #include <vector>
 #include "internal.cuh"
 
@@ -95,6 +96,48 @@ static LikWs lik_ws(int n, int q, int d) {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Library-owned streams for the chunk pipeline of the batched criterion: one set per (device, caller stream).
+constexpr int BATCH_SLOTS = 4;
+struct BatchStreams {
+    cudaStream_t caller = nullptr;
+    int dev = -1;
+    cudaStream_t q[BATCH_SLOTS] = {};
+    cudaEvent_t fork = nullptr, join[BATCH_SLOTS] = {};
+    bool ok = false;
+};
+static std::mutex g_bs_mutex;
+static std::vector<BatchStreams*> g_bs_sets;
+static BatchStreams* batch_streams(cudaStream_t caller) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_bs_mutex);
+    for (BatchStreams* b : g_bs_sets)
+        if (b->dev == dev && b->caller == caller) return b;
+    BatchStreams* b = new BatchStreams();
+    b->caller = caller;
+    b->dev = dev;
+    b->ok = cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < BATCH_SLOTS && b->ok; ++k)
+        b->ok = cudaStreamCreateWithFlags(&b->q[k], cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&b->join[k], cudaEventDisableTiming) == cudaSuccess;
+    g_bs_sets.push_back(b);
+    return b;
+}
+
+// FP64 tensor pipe issue-rate probe: every warp keeps 8 independent DMMA.8x8x4 chains in registers.
+__global__ void __launch_bounds__(512, 1) dmma_peak_kernel(double* sink, int iters, double a, double b) {
+    double c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c0[i] = c1[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c0[i], c1[i], a, b);
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += c0[i] + c1[i];
+    if (acc == 123.456) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;  // keeps the chains alive
+}
+
 }  // namespace gpmp
 
 using namespace gpmp;
@@ -104,8 +147,17 @@ extern "C" {
 int gpmp_abi_version(void) { return 1; }
 unsigned long long gpmp_launch_count(void) { return g_launches; }
 
+int gpmp_measure_dmma_peak(int ctas, int iters, double* sink_dev, double* flops_out, void* stream) {
+    if (ctas <= 0 || iters <= 0 || !sink_dev) return GPMP_ERR_ARG;
+    dmma_peak_kernel<<<ctas, 512, 0, (cudaStream_t)stream>>>(sink_dev, iters, 1.0000001, 1e-9);
+    GPMP_CHECK_LAUNCH();
+    // 16 warps x 8 DMMAs per round, 8 x 8 x 4 multiply-adds each
+    if (flops_out) *flops_out = (double)ctas * 16.0 * 8.0 * (double)iters * 2.0 * 8.0 * 8.0 * 4.0;
+    return GPMP_OK;
+}
+
 int gpmp_prof_enable(int enable) {
-    g_prof.enabled = enable ? 1 : 0;
+    g_prof.enabled = enable == 2 ? 2 : (enable ? 1 : 0);  // 2: also serialise the look-ahead streams
     return GPMP_OK;
 }
 // development hook (not part of the header): rows [class, stream id, start ms, duration ms] of every launch
@@ -241,7 +293,7 @@ int gpmp_potrf(double* A_dev, int n, int nrows, long long lda, void* work_dev, s
     char* base = static_cast<char*>(work_dev);
     return potrf_core(A_dev, lda, 0, n, nrows, w.NB, (double*)(base + w.off_tlo), (double*)(base + w.off_tup), 0,
                       (double*)(base + w.off_w), 0, info_dev, 0, 1, (cudaStream_t)stream,
-                      (double*)(base + w.off_tsub));
+                      (double*)(base + w.off_tsub), 0, ceil_div(n > 0 ? n : 1, 128));
 }
 
 int gpmp_potri(const double* L_dev, int n, long long ldl, const void* potrf_work_dev, double* Tlo_dev,
@@ -349,7 +401,7 @@ int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk
     char* pb = base + w.off_potrf;
     rc = potrf_core((double*)(base + w.off_A), w.lda, 0, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo),
                     (double*)(pb + w.pw.off_tup), 0, (double*)(pb + w.pw.off_w), 0, info_dev, 0, 1, s,
-                    (double*)(pb + w.pw.off_tsub));
+                    (double*)(pb + w.pw.off_tsub), 0, ceil_div(n, 128));
     if (rc) return rc;
     return lik_finalize(n, q, w, base, out_dev, info_dev, s);
 }
@@ -686,40 +738,76 @@ int gpmp_criterion_batched(const gpmp_cov_spec* spec, const double* theta_dev, i
     MaternDev* mdev = (MaternDev*)(pbase + (size_t)cap * (w.per_A + 2 * w.per_T + w.per_W));
     double* Tsub = (double*)(pbase + (size_t)cap * (w.per_A + 2 * w.per_T + w.per_W + w.per_mdev));
     const long long sA = (long long)(w.per_A / 8), sT = (long long)(w.per_T / 8), sW = (long long)(w.per_W / 8);
+    const long long sTsub = (long long)(w.per_tsub / 8);
     int rc;
     if (cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)N, s) != cudaSuccess) return GPMP_ERR_CUDA;
     const int w_theta = 1 + spec->noise + spec->d;
-    for (long long c0 = 0; c0 < N; c0 += cap) {
-        const int nb = (int)((N - c0) < cap ? (N - c0) : cap);
-        rc = launch_prep_theta(spec, theta_dev + c0 * w_theta, nb, 1, mdev, s);
+    // The particles in flight are split over up to BATCH_SLOTS workspace slots, each served by its own
+    // library-owned stream: the phases of one chunk are bound by different things (K build: instruction issue;
+    // tile kernel: the pivot chain's latency; panel solve / SYRK: the DMMA pipe), so chunks at different phases
+    // share the SMs instead of taking turns.  A slot is always used on the same stream, which orders its reuse.
+    cudaStream_t slot_stream[BATCH_SLOTS];
+    int nslots = (int)(cap / 256);
+    nslots = nslots < 1 ? 1 : (nslots > BATCH_SLOTS ? BATCH_SLOTS : nslots);
+    if (prof().enabled == 2) nslots = 1;  // serialised profiling pass: exclusive kernel times
+    BatchStreams* bs = nslots > 1 ? batch_streams(s) : nullptr;
+    if (!bs || !bs->ok) nslots = 1;
+    const long long chunk = (cap + nslots - 1) / nslots;
+    for (int k = 0; k < nslots; ++k) slot_stream[k] = nslots > 1 ? bs->q[k] : s;
+    if (q > 0) {
+        // the raw basis rows and sum log R0_ii are shared by every chunk: written once, on the caller's stream,
+        // before the fork
+        LoadRowsArgs l0;
+        l0.P = P_dev; l0.z = z_dev; l0.n = n; l0.q = q;
+        l0.rows = A + (long long)n * w.lda; l0.ld = w.lda; l0.stride = sA;
+        l0.p0rows = p0rows; l0.ld0 = w.lda;
+        rc = launch_load_rows(l0, 1, s);
         if (rc) return rc;
-        // MaternDev entries are packed (sizeof), not per_mdev-strided
-        rc = launch_matern_cov(spec, mdev, nb, sA, x_dev, n, nullptr, n, A, w.lda, COV_SYM_LOWER, 0, s);
+        rc = launch_logdet_r0(p0rows, p0work, w.lda, n, q, ldr0, s);
+        if (rc) return rc;
+    }
+    if (nslots > 1) {
+        if (cudaEventRecord(bs->fork, s) != cudaSuccess) return GPMP_ERR_CUDA;
+        for (int k = 0; k < nslots; ++k)
+            if (cudaStreamWaitEvent(slot_stream[k], bs->fork, 0) != cudaSuccess) return GPMP_ERR_CUDA;
+    }
+    int slot = 0;
+    for (long long c0 = 0; c0 < N; c0 += chunk, slot = (slot + 1) % nslots) {
+        const int nb = (int)((N - c0) < chunk ? (N - c0) : chunk);
+        cudaStream_t cs = slot_stream[slot];
+        const long long e0 = (long long)slot * chunk;  // first workspace entry of this slot
+        double* As = A + e0 * sA;
+        MaternDev* ms = mdev + e0;  // MaternDev entries are packed (sizeof), not per_mdev-strided
+        rc = launch_prep_theta(spec, theta_dev + c0 * w_theta, nb, 1, ms, cs);
+        if (rc) return rc;
+        rc = launch_matern_cov(spec, ms, nb, sA, x_dev, n, nullptr, n, As, w.lda, COV_SYM_LOWER, 0, cs);
         if (rc) return rc;
         LoadRowsArgs lr;
         lr.P = P_dev; lr.z = z_dev; lr.n = n; lr.q = q;
-        lr.rows = A + (long long)n * w.lda; lr.ld = w.lda; lr.stride = sA;
-        lr.p0rows = (q > 0 && c0 == 0) ? p0rows : nullptr; lr.ld0 = w.lda;
-        rc = launch_load_rows(lr, nb, s);
+        lr.rows = As + (long long)n * w.lda; lr.ld = w.lda; lr.stride = sA;
+        lr.p0rows = nullptr; lr.ld0 = w.lda;
+        rc = launch_load_rows(lr, nb, cs);
         if (rc) return rc;
-        rc = potrf_core(A, w.lda, sA, n, w.nrows, w.NB, Tlo, Tup, sT, W, sW, info_dev + c0, 1, nb, s, Tsub,
-                        (long long)(w.per_tsub / 8));
+        rc = potrf_core(As, w.lda, sA, n, w.nrows, w.NB, Tlo + e0 * sT, Tup + e0 * sT, sT, W + e0 * sW, sW,
+                        info_dev + c0, 1, nb, cs, Tsub + e0 * sTsub, sTsub, 1);
         if (rc) return rc;
         FinalizeArgs f;
         f.rows = lr.rows; f.ld = w.lda; f.strideRows = sA;
         f.p0rows = p0rows; f.ld0 = w.lda; f.p0work = p0work; f.strideP0 = 0;
-        f.Ldiag = A; f.ldl = w.lda; f.strideL = sA;
+        f.Ldiag = As; f.ldl = w.lda; f.strideL = sA;
         f.n = n; f.q = q;
         f.Rt = nullptr; f.strideRt = 0;
         f.info = info_dev + c0; f.strideInfo = 1;
         f.out = values_dev + c0; f.strideOut = 1;
         f.ldr0_in = q > 0 ? ldr0 : nullptr;
-        if (c0 == 0 && q > 0) {
-            rc = launch_logdet_r0(p0rows, p0work, w.lda, n, q, ldr0, s);
-            if (rc) return rc;
-        }
-        rc = launch_finalize(f, nb, s);
+        rc = launch_finalize(f, nb, cs);
         if (rc) return rc;
+    }
+    if (nslots > 1) {
+        for (int k = 0; k < nslots; ++k)
+            if (cudaEventRecord(bs->join[k], slot_stream[k]) != cudaSuccess ||
+                cudaStreamWaitEvent(s, bs->join[k], 0) != cudaSuccess)
+                return GPMP_ERR_CUDA;
     }
     return GPMP_OK;
 }

@@ -38,7 +38,9 @@ int launch_maternp_elementwise(int p, const double* h, double* k, double* dk, lo
 int potrf_block_size(int n);
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream, double* Tsub = nullptr, long long strideTsub = 0);
+               cudaStream_t stream, double* Tsub = nullptr, long long strideTsub = 0, int tsub_tiles = 0);
+// Tsub: block-diagonal (32x32) tile inverses for the substitution solve; tsub_tiles = 128x128 tiles it holds per
+// matrix (ceil(n / 128) for the look-ahead path of a single matrix, 1 for the batched value-only path)
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
                double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream, int batch = 1,
                long long strideL = 0, long long strideTc = 0, long long strideT = 0);
@@ -70,7 +72,8 @@ struct FinalizeArgs {
     double* p0work; long long strideP0;                 // q x ld0 scratch per batch entry (may alias for batch 1)
     const double* Ldiag; long long ldl; long long strideL;  // L (diag read at i*(ldl+1))
     int n, q;
-    double* out; long long strideOut;       // [value, logdet, quad, 2 sum log L_ii, logdetR~*2, logdetR0*2]
+    double* out; long long strideOut;       // [value, logdet, quad, 2 sum log L_ii, logdetR~*2, logdetR0*2, info]: 7 slots when
+                                            // strideOut is 0 or >= 7, the value alone otherwise
     double* Rt; long long strideRt;         // optional (q+1) x (q+1): upper triangle = R~ with the z column
     const int* info; long long strideInfo;  // non-zero -> value = +inf
     const double* ldr0_in;                  // optional precomputed sum log R0_ii (skips the raw-basis pass)

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finalize_kernel(const Finalize
         if (bad || !(val == val)) val = INFINITY;
         double* o = a.out + b * a.strideOut;
         o[0] = val;
-        if (a.strideOut >= 6 || a.strideOut == 0) {
+        if (a.strideOut >= 7 || a.strideOut == 0) {  // the 7-slot record (value first)
             o[1] = logdet; o[2] = quad; o[3] = ldl2; o[4] = 2.0 * ld_rt; o[5] = 2.0 * ld_r0;
             o[6] = (double)bad;  // info mirrored as a double: one 64-byte readback serves the host wrapper
         }

@@ -21,6 +21,8 @@
 // (trsm_tile_kernel) instead of the tile inverse; batched value-only sweeps use the packed factor-only tile
 // kernel (two tiles per SM) and one solve CTA per matrix; the same pieces serve the panel-partitioned
 // multi-GPU loop (dist_*).
+#include <cstdlib>
+#include <mutex>
 #include <vector>
 #include "internal.cuh"
 
@@ -1088,8 +1090,17 @@ static int launch_copy_panel(const CopyPanelArgs& a, int batch, cudaStream_t str
     return GPMP_OK;
 }
 
+// development knobs (unset in production): GPMP_DEV_NB overrides the column-group width for n > 1024,
+// GPMP_DEV_LA the look-ahead depth (1 .. LA_DEPTH)
+static int dev_env(const char* name) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+
 int potrf_block_size(int n) {
     if (n <= 1024) return 128;
+    static const int forced = dev_env("GPMP_DEV_NB");
+    if (forced == 256 || forced == 512) return forced;
     if (n <= 4096) return 256;
     return 512;
 }
@@ -1306,30 +1317,49 @@ static int trailing_update(const PotrfCtx& c, int k, const double* Pnl, long lon
     return launch_gemm_nt(h, stream);
 }
 
-// Library-owned side stream (high priority) and events for the look-ahead pipeline.
+// Library-owned streams and events of the look-ahead pipeline: one set per (device, caller stream), so two
+// caller streams that factor concurrently never share chain streams or reuse each other's events (the ABI is
+// re-entrant per (stream, workspace)).  The sets live for the life of the process.
+constexpr int LA_DEPTH = 4;  // look-ahead depth: the chain may run this many column groups ahead of the bulk
 struct LookAhead {
+    cudaStream_t caller = nullptr;
+    int dev = -1;
     cudaStream_t side = nullptr;    // the chain: what the next tile factorisation is waiting for
     cudaStream_t helper = nullptr;  // updates inside the next column group that are not on the chain
+    cudaStream_t ahead[LA_DEPTH] = {};  // look-ahead updates: group g receives panels g-D .. g-2 on ahead[g % D]
     std::vector<cudaEvent_t> ev;
-    int dev = -1;
     bool ok = false;
 };
-static LookAhead& lookahead(int nevents) {
-    static LookAhead la;
+static std::mutex g_la_mutex;
+static std::vector<LookAhead*> g_la_sets;
+
+static LookAhead* lookahead(cudaStream_t caller, int nevents) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (la.side == nullptr || la.dev != dev) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
-                cudaStreamCreateWithPriority(&la.helper, cudaStreamNonBlocking, hi) == cudaSuccess;
-        la.dev = dev;
-        la.ev.clear();
+    LookAhead* la = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_la_mutex);
+        for (LookAhead* c : g_la_sets)
+            if (c->dev == dev && c->caller == caller) { la = c; break; }
+        if (!la) {
+            la = new LookAhead();
+            la->caller = caller;
+            la->dev = dev;
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const int mid = hi < lo ? hi + 1 : hi;  // one step below the chain when the device has the range
+            la->ok = cudaStreamCreateWithPriority(&la->side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                     cudaStreamCreateWithPriority(&la->helper, cudaStreamNonBlocking, hi) == cudaSuccess;
+            for (int i = 0; i < LA_DEPTH && la->ok; ++i)
+                la->ok = cudaStreamCreateWithPriority(&la->ahead[i], cudaStreamNonBlocking, mid) == cudaSuccess;
+            g_la_sets.push_back(la);
+        }
     }
-    while (la.ok && (int)la.ev.size() < nevents) {
+    // a set is only ever used from its caller stream's thread of control, so growing it needs no lock
+    while (la->ok && (int)la->ev.size() < nevents) {
         cudaEvent_t e;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { la.ok = false; break; }
-        la.ev.push_back(e);
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { la->ok = false; break; }
+        la->ev.push_back(e);
     }
     return la;
 }
@@ -1338,13 +1368,18 @@ static LookAhead& lookahead(int nevents) {
 //   A      (nrows x lda)            in: lower of K (+ extra rows); out: L both-ways (+ whitened rows)
 //   Tlo/Tup compact diagonal-block inverses: nblk blocks of NB x NB (ld NB), block b at b*NB*NB
 //   W      panel scratch: TWO buffers of max(nrows, NB) x NB (ld NB) per batch entry, the second at
-//          W + Wrows*NB (look-ahead keeps the previous group's panel alive while the next one is built)
-// Single matrices with several column groups run a depth-1 look-ahead: the main stream does the bulk of
-// every K=NB trailing update while a high-priority side stream updates the next group's columns and
-// runs its 128-wide steps, so the latency-bound chain hides behind the big SYRK.
+//          W + Wrows*NB (the in-group updates of one group read its buffer while the next group fills the other)
+// Single matrices with several column groups run a depth-D look-ahead (D = LA_DEPTH): the caller's stream does
+// the bulk of every K=NB trailing update -- the column groups more than D ahead -- while library-owned priority
+// streams bring the next D groups up to date one (panel, group) product at a time and run the 128-wide steps of
+// the next group.  The latency-bound chain therefore runs up to D groups ahead of the bulk while the trailing
+// matrix is large, and that lead pays for the tail of the factorisation, where a group's bulk update is shorter
+// than its chain (n = 8192: sum of the chain steps 4.8 ms, sum of the updates 5.9 ms; with depth 1 the two
+// alternate instead of overlapping).  Trailing updates read the solved panel straight from A (its final place;
+// nothing writes it again), so the lagging bulk never holds a panel buffer.
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream, double* Tsub, long long strideTsub) {
+               cudaStream_t stream, double* Tsub, long long strideTsub, int tsub_tiles) {
     if (n <= 0) return GPMP_OK;
     // batched value-only runs: the few whitening rows below the matrix travel as the solve kernel's extra strip
     const int nextra = (batch > 1 && Tsub != nullptr && nrows > n && nrows - n <= TS_EXTRA) ? nrows - n : 0;
@@ -1354,9 +1389,13 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
     const long long wrows = nrows > NB ? nrows : NB;
     double* Wb[2] = {W, W + wrows * NB};
     int rc;
-    const bool pipelined = batch == 1 && nblk >= 3 && NB > PT && Tsub != nullptr;
-    LookAhead* la = pipelined ? &lookahead(3 + 10 * (nblk + 2)) : nullptr;
+    // the pipelined path keeps one block-diagonal inverse tile per 128 columns: the caller must have sized Tsub
+    // for that (tsub_tiles); the batched value-only callers pass ONE tile per matrix and never come here
+    const bool pipelined = batch == 1 && nblk >= 3 && NB > PT && Tsub != nullptr && tsub_tiles >= ceil_div(n, PT);
+    const int EV = 11;
+    LookAhead* la = pipelined ? lookahead(stream, 4 + 2 * LA_DEPTH + EV * (nblk + LA_DEPTH + 2)) : nullptr;
     if (!pipelined || !la->ok) {
+        if (batch == 1 && Tsub != nullptr && tsub_tiles < ceil_div(n, PT)) c.Tsub = nullptr;  // full tile inverses
         for (int k = 0; k < n; k += NB) {
             const int gw = min(NB, n - k), r0 = k + gw;
             rc = group_panel(c, k, Wb[0], strideW, stream);
@@ -1367,14 +1406,22 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
         }
         return block_inverses(c, Wb[0], strideW, stream);
     }
-    // Three streams.  s (caller's): the bulk K=NB updates.  B (chain): only what the next tile factorisation
-    // waits for -- the update of the next 128 columns, the tile kernel, the solve below it.  H (helper): the
-    // other updates inside the next group (its remaining columns from the previous panel and from its own
-    // earlier steps).  Events order every read-modify-write of a column block.
-    cudaStream_t s = stream, B = la->side, H = la->helper;
-    const int EV = 10;
-    auto ev = [&](int g, int i) { return la->ev[2 + (g + 1) * EV + i]; };  // g = -1 .. nblk-1
-    enum { E_PANEL = 0, E_REST = 1, E_HEADREST = 2, E_TRSM = 3 /* +c, c<4 */, E_IN = 7 /* +c, c<2 */ };
+    // Streams.  s (caller's): the bulk K=NB updates.  B (chain): only what the next tile factorisation waits
+    // for -- the update of the next 128 columns, the tile kernel, the solve below it.  H (helper): the other
+    // updates inside the next group (its remaining columns from the previous panel and from its own earlier
+    // steps) and the tile inverses.  Q[g % D]: the updates of group g by the panels g-D .. g-2, in that order
+    // (stream order is the read-modify-write order of the group's columns).  Events order every other
+    // read-modify-write of a column block.
+    static const int forced_depth = dev_env("GPMP_DEV_LA");
+    const int D = min(forced_depth > 0 ? min(forced_depth, LA_DEPTH) : LA_DEPTH, nblk - 1);
+    // profiling mode 2 (gpmp_prof_enable(2)): the same launches, all on the caller's stream, so the per-class
+    // CUDA-event times are exclusive kernel times
+    const bool serial = prof().enabled == 2;
+    cudaStream_t s = stream, B = serial ? stream : la->side, H = serial ? stream : la->helper;
+    cudaStream_t Q[LA_DEPTH];
+    for (int i = 0; i < LA_DEPTH; ++i) Q[i] = serial ? stream : la->ahead[i];
+    auto ev = [&](int g, int i) { return la->ev[4 + 2 * LA_DEPTH + g * EV + i]; };  // g = 0 .. nblk + D
+    enum { E_PANEL = 0, E_REST = 1, E_HEADREST = 2, E_TRSM = 3 /* +c, c<4 */, E_IN = 7 /* +c, c<2 */, E_G2 = 9 };
     // steps of the group starting at k0 (group index g); head_rest: wait for the helper's head update first
     auto run_group = [&](int g, int k0, double* Wn, bool head_rest) -> int {
         const int gw = min(NB, n - k0), nblocks = ceil_div(gw, PT);
@@ -1412,32 +1459,50 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
     if (cudaEventRecord(la->ev[0], s) != cudaSuccess || cudaStreamWaitEvent(B, la->ev[0], 0) != cudaSuccess ||
         cudaStreamWaitEvent(H, la->ev[0], 0) != cudaSuccess)
         return GPMP_ERR_CUDA;
+    for (int i = 0; i < D; ++i)
+        if (cudaStreamWaitEvent(Q[i], la->ev[0], 0) != cudaSuccess) return GPMP_ERR_CUDA;
     rc = run_group(0, 0, Wb[0], false);
     if (rc) return rc;
     for (int b = 0; b < nblk; ++b) {
         const int k = b * NB, gw = min(NB, n - k), r0 = k + gw;
         if (nrows - r0 <= 0) break;
-        const double* Pk = Wb[b & 1] + (long long)gw * NB;  // solved panel rows r0.. of group b
-        const int nb_next = min(NB, n - r0);  // width of the next group (0 when only extra rows remain)
+        const double* Pk = A + (long long)r0 * lda + k;  // solved panel rows r0.. of group b, in place
+        const int Nn = n - r0;                // trailing columns
+        const int nb_next = min(NB, Nn);      // width of the next group (0 when only extra rows remain)
         const int head0 = min(PT, nb_next);
-        // updates of the next group's columns by panel b: first 128 columns on the chain, the rest on the helper
+        // group b+1 by panel b: first 128 columns on the chain, the rest on the helper; both behind the update
+        // of that group by panel b-1 (a look-ahead product when D >= 2, part of the bulk otherwise)
         if (b > 0) {
-            cudaStreamWaitEvent(B, ev(b - 1, E_REST), 0);
-            cudaStreamWaitEvent(H, ev(b - 1, E_REST), 0);
+            cudaEvent_t dep = D >= 2 ? ev(b + 1, E_G2) : ev(b - 1, E_REST);
+            cudaStreamWaitEvent(B, dep, 0);
+            cudaStreamWaitEvent(H, dep, 0);
         }
         if (nb_next > 0) {
-            rc = trailing_update(c, k, Pk, NB, strideW, 0, head0, B);
+            rc = trailing_update(c, k, Pk, lda, 0, 0, head0, B);
             if (rc) return rc;
             if (nb_next > head0) {
                 cudaStreamWaitEvent(H, ev(b, E_PANEL), 0);
-                rc = trailing_update(c, k, Pk, NB, strideW, head0, nb_next, H);
+                rc = trailing_update(c, k, Pk, lda, 0, head0, nb_next, H);
                 if (rc) return rc;
                 cudaEventRecord(ev(b + 1, E_HEADREST), H);
             }
         }
-        // bulk of the trailing update on the main stream
+        // groups b+2 .. b+D by panel b, one product each on the group's own stream; the farthest one follows
+        // the bulk update by panel b-1, which still covered that group
+        for (int d = 2; d <= D; ++d) {
+            const int c0 = (d - 1) * NB;
+            if (c0 >= Nn) break;
+            const int c1 = min(d * NB, Nn), g = b + d;
+            cudaStream_t q = Q[g % D];
+            cudaStreamWaitEvent(q, ev(b, E_PANEL), 0);
+            if (d == D && b > 0) cudaStreamWaitEvent(q, ev(b - 1, E_REST), 0);
+            rc = trailing_update(c, k, Pk, lda, 0, c0, c1, q);
+            if (rc) return rc;
+            if (d == 2) cudaEventRecord(ev(g, E_G2), q);
+        }
+        // bulk of the trailing update (the groups beyond the look-ahead window) on the caller's stream
         cudaStreamWaitEvent(s, ev(b, E_PANEL), 0);
-        rc = trailing_update(c, k, Pk, NB, strideW, nb_next, -1, s);
+        rc = trailing_update(c, k, Pk, lda, 0, min(Nn, D * NB), -1, s);
         if (rc) return rc;
         cudaEventRecord(ev(b, E_REST), s);
         // next group's steps
@@ -1451,6 +1516,10 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
         return GPMP_ERR_CUDA;
     if (cudaEventRecord(la->ev[2], H) != cudaSuccess || cudaStreamWaitEvent(s, la->ev[2], 0) != cudaSuccess)
         return GPMP_ERR_CUDA;
+    for (int i = 0; i < D; ++i)
+        if (cudaEventRecord(la->ev[4 + i], Q[i]) != cudaSuccess ||
+            cudaStreamWaitEvent(s, la->ev[4 + i], 0) != cudaSuccess)
+            return GPMP_ERR_CUDA;
     return block_inverses(c, Wb[0], strideW, s);
 }
 

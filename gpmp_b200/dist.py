@@ -56,7 +56,7 @@ def reml_value_distributed(model, covparam, xi, zi, group=None, want_grad=False)
     xi_, zi_, _ = core._ensure_shapes_and_type(xi=xi, zi=zi)
     P = model._basis(xi_) if model.meantype == "linear_predictor" else None
     if model.meantype == "parameterized":
-        zi_ = zi_ - ops.to_device(model.mean(xi_, num.asparam(model.meanparam))).reshape(-1)
+        zi_ = zi_ - model.mean_values(xi_, num.asparam(model.meanparam)).reshape(-1)
     K, fused = model._same_set_cov(xi_, num.asparam(covparam))
     with torch.no_grad():
         if fused:

@@ -121,18 +121,14 @@ def maternp_covariance(x, y, p, param, pairwise=False):
     return maternp_covariance_it(x, y, p, param, pairwise)
 
 
-# parameter selection front-ends live in gpmp.kernel in the reference (kernel/__init__.py); same names here
+# initial guesses live in gpmp.kernel in the reference (kernel/__init__.py); same names here.  The optimiser
+# front-ends (select_parameters_with_*) are GPmp's own: bind this library with gpmp_b200.dropin.install().
 from .selection import (  # noqa: E402,F401
     anisotropic_parameters_initial_guess,
     anisotropic_parameters_initial_guess_constant_mean,
     anisotropic_parameters_initial_guess_zero_mean,
-    autoselect_parameters,
-    make_selection_criterion_with_gradient,
+    multistart_reml,
     negative_log_likelihood,
     negative_log_likelihood_zero_mean,
     negative_log_restricted_likelihood,
-    select_parameters_with_criterion,
-    select_parameters_with_ml,
-    select_parameters_with_ml_zero_mean,
-    select_parameters_with_reml,
 )

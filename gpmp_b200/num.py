@@ -8,6 +8,7 @@ typically need are thin device-placing wrappers over torch.
 """
 from __future__ import annotations
 
+import builtins
 import math
 
 import numpy as np
@@ -184,95 +185,99 @@ def solve_triangular(A, B, trans=0, lower=False, unit_diagonal=False, overwrite_
     return x.reshape(-1) if vec else x
 
 
-# ---- autograd wrappers (torch_backend.py:506-604) ------------------------------------------------------
-def grad(f):
-    def f_grad(x):
-        x = asparam(x).detach().clone().requires_grad_(True)
-        y = f(x)
-        return torch.autograd.grad(y, x, allow_unused=True)[0]
+# ---- differentiation helpers: the names GPmp's drivers call (API of torch_backend.py:506-604) -------------------------
+# Parameter vectors are HOST leaves here (SciPy hands them over and wants the gradient back on the host); the
+# criterion they feed is a custom op whose backward runs on the device.
+_LINALG_MARKERS = ("not positive definite", "not positive-definite", "singular", "cholesky", "factorization")
 
-    return f_grad
+
+def linalg_failure(exc):
+    """True for the failures GPmp's optimiser maps to criterion = +inf (a covariance matrix that is not positive
+    definite): torch's LinAlgError, or a RuntimeError whose text names such a failure."""
+    if isinstance(exc, torch.linalg.LinAlgError):
+        return True
+    text = str(exc).lower()
+    return isinstance(exc, RuntimeError) and builtins.any(m in text for m in _LINALG_MARKERS)
+
+
+_is_linalg_exception = linalg_failure  # the reference's private name, kept for code written against it
+
+
+def _host_leaf(p):
+    return asparam(p).detach().clone().requires_grad_(True)
+
+
+def _scalar_of(y):
+    if not torch.is_tensor(y):
+        raise TypeError(f"the criterion returned {type(y).__name__}; a 0-d torch tensor is required")
+    if y.numel() != 1:
+        raise ValueError(f"the criterion returned {y.numel()} values; a scalar is required")
+    return y.reshape(())
 
 
 def value_and_grad(f, x):
-    """(f(x), df/dx); a non-finite value comes back with a zero gradient (torch_backend.py:516-533)."""
+    """(f(x), df/dx) as detached host tensors.  A non-finite value comes back with a zero gradient -- the
+    convention NUTS / SVGD rely on (torch_backend.py:528-529)."""
+    leaf = _host_leaf(x)
     with torch.enable_grad():
-        x_ = asparam(x).detach().requires_grad_(True)
-        y = f(x_)
-        if not torch.is_tensor(y):
-            raise ValueError("f(x) must return a torch scalar tensor.")
-        if y.ndim != 0:
-            if y.numel() == 1:
-                y = y.reshape(())
-            else:
-                raise ValueError("f(x) must return a scalar.")
-        if not torch.isfinite(y):
-            return y.detach(), torch.zeros_like(x_).detach()
-        (g,) = torch.autograd.grad(y, x_, create_graph=False, allow_unused=True)
-        if g is None:
-            g = torch.zeros_like(x_)
-    return y.detach(), g.detach()
+        y = _scalar_of(f(leaf))
+        g = None
+        if bool(torch.isfinite(y)):
+            (g,) = torch.autograd.grad(y, leaf, allow_unused=True)
+    return y.detach(), (torch.zeros_like(leaf) if g is None else g.detach())
 
 
-def _is_linalg_exception(exc):
-    if isinstance(exc, torch.linalg.LinAlgError):
-        return True
-    msg = str(exc).lower()
-    return builtins_any(k in msg for k in ("singular", "not positive definite", "not positive-definite",
-                                           "cholesky", "factorization"))
-
-
-def builtins_any(it):
-    for v in it:
-        if v:
-            return True
-    return False
+def grad(f):
+    """x -> df/dx."""
+    return lambda x: value_and_grad(f, x)[1]
 
 
 class DifferentiableSelectionCriterion:
-    """Same life-cycle as torch_backend.py:547-604: `evaluate_pre_grad(p)` keeps the scalar with its graph
-    and returns a float, `gradient(p)` differentiates it.  p stays a host tensor; x, z are uploaded once."""
+    """The object `make_selection_criterion_with_gradient` (kernel/parameter_selection.py:116-124) builds around a
+    criterion f(p, x, z): SciPy calls `evaluate_pre_grad(p)` for the value (a float) and then `gradient(p)` at the
+    same p; samplers call `evaluate_no_grad`.  Same four methods as torch_backend.py:547-604.  The data are
+    uploaded once here; p stays a host vector."""
 
     def __init__(self, f, x, z):
-        self.f = f
-        self.x = asarray(x)
-        self.z = asarray(z)
-        self._p_value = None
-        self._f_value = None
+        self.f, self.x, self.z = f, asarray(x), asarray(z)
+        self._pending = None  # (host leaf, criterion scalar with its graph) of the last evaluate_pre_grad
 
-    def __call__(self, p):
-        return self.evaluate(p)
+    def _run(self, p):
+        """Criterion at p; a covariance that is not positive definite counts as +inf."""
+        try:
+            return self.f(p, self.x, self.z)
+        except Exception as exc:  # noqa: BLE001 - everything that is not a linear-algebra failure propagates
+            if linalg_failure(exc):
+                return None
+            raise
 
     def evaluate(self, p):
         return self.f(p, self.x, self.z)
 
+    __call__ = evaluate
+
     def evaluate_no_grad(self, p):
-        p = asparam(p)
-        try:
-            with torch.no_grad():
-                return self.f(p, self.x, self.z)
-        except Exception as exc:  # noqa: BLE001 - same mapping as the reference
-            if _is_linalg_exception(exc):
-                return inf
-            raise
+        with torch.no_grad():
+            v = self._run(asparam(p))
+        return inf if v is None else v
 
     def evaluate_pre_grad(self, p):
-        self._p_value = asparam(p).detach().clone().requires_grad_(True)
-        try:
-            self._f_value = self.f(self._p_value, self.x, self.z)
-            return self._f_value.item()
-        except Exception as exc:  # noqa: BLE001
-            if _is_linalg_exception(exc):
-                self._f_value = torch.tensor(float("inf"), requires_grad=True)
-                return self._f_value.item()
-            raise
+        leaf = _host_leaf(p)
+        v = self._run(leaf)
+        if v is None:
+            v = safe_inf()
+        self._pending = (leaf, v)
+        return v.item()
 
     def gradient(self, p, retain=False, allow_unused=True):
-        if self._f_value is None:
-            raise ValueError("Call 'evaluate_pre_grad(p)' before 'gradient(p)'")
-        if not torch.equal(asparam(p), self._p_value.detach()):
-            raise ValueError("The input 'p' in 'gradient' must be the same as in 'evaluate'")
-        g = torch.autograd.grad(self._f_value, self._p_value, retain_graph=retain, allow_unused=allow_unused)[0]
+        if self._pending is None:
+            raise ValueError("gradient(p) needs a preceding evaluate_pre_grad(p)")
+        leaf, v = self._pending
+        if not torch.equal(asparam(p), leaf.detach()):
+            raise ValueError("gradient(p) was called at a different p than evaluate_pre_grad(p)")
+        if not bool(torch.isfinite(v)) or v.grad_fn is None:
+            return torch.zeros_like(leaf)
+        (g,) = torch.autograd.grad(v, leaf, retain_graph=retain, allow_unused=allow_unused)
         if g is None:
-            raise RuntimeError("Gradient is None.")
+            raise RuntimeError("the criterion does not depend on p")
         return g

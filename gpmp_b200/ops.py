@@ -656,10 +656,44 @@ def criterion_batched_workspace(n, q, N, max_bytes=None):
     return _workspace(lib().gpmp_criterion_batched_bytes(n, q, int(nb)))
 
 
+def _batched_operands(theta, x, z, P, noise):
+    """Device, dtype, contiguity and shape checks shared by the batched entry points (the C side strides theta by
+    1 + noise + d and trusts every pointer).  An isotropic parameter row [log s2, (log tau2,) log(1/rho)] is
+    expanded to d length-scale columns; the flag tells the caller to fold the gradient back."""
+    theta = to_device(theta)
+    x = to_device(x)
+    z = to_device(z)
+    P = to_device(P)
+    if theta.dim() != 2:
+        raise _abi.GpmpError(f"theta must be a 2-D (N, 1+noise+d) array, got shape {tuple(theta.shape)}")
+    if x.dim() not in (2, 3):
+        raise _abi.GpmpError(f"x must be (n, d) or (N, n, d), got shape {tuple(x.shape)}")
+    d = x.shape[-1]
+    if d > _abi.MAX_DIM:
+        raise _abi.GpmpError(f"input dimension {d} exceeds {_abi.MAX_DIM}")
+    head = 1 + int(bool(noise))
+    iso = False
+    if theta.shape[1] == head + 1 and d > 1:
+        theta = torch.cat((theta[:, :head], theta[:, head:].expand(-1, d)), dim=1).contiguous()
+        iso = True
+    if theta.shape[1] != head + d:
+        raise _abi.GpmpError(f"theta has {theta.shape[1]} columns; expected 1 + noise + d = {head + d} "
+                             f"(or {head + 1} for an isotropic kernel)")
+    if P is not None:
+        if P.dim() != 2 or P.shape[0] != x.shape[-2]:
+            raise _abi.GpmpError(f"mean basis must be (n, q) with n = {x.shape[-2]}, got {tuple(P.shape)}")
+        if P.shape[1] > _abi.MAX_Q:
+            raise _abi.GpmpError(f"mean basis has {P.shape[1]} columns; at most {_abi.MAX_Q} are supported")
+    return theta, x, z, P, iso
+
+
 def criterion_batched(theta, x, z, P, p, noise=False, max_bytes=None, work=None):
-    """N criterion values at the rows of theta (N x (1+noise+d)) on fixed (x, z, P); device tensors in,
-    (values[N], info[N]) device tensors out.  `work` (optional) is a reusable workspace from
-    criterion_batched_workspace; it decides how many particles are in flight per chunk."""
+    """N criterion values at the rows of theta (N x (1+noise+d)) on fixed (x, z, P); (values[N], info[N]) device
+    tensors out.  `work` (optional) is a reusable workspace from criterion_batched_workspace; it decides how many
+    particles are in flight per chunk."""
+    theta, x, z, P, _ = _batched_operands(theta, x, z, P, noise)
+    if x.dim() != 2 or z.dim() != 1 or z.shape[0] != x.shape[0]:
+        raise _abi.GpmpError("criterion_batched takes one shared point set x (n, d) and observations z (n,)")
     N = theta.shape[0]
     n, d = x.shape
     q = 0 if P is None else P.shape[1]
@@ -691,6 +725,7 @@ def criterion_batched_grad(theta, x, z, P, p, noise=False, max_bytes=None, work=
     (N, n, d) one point set per entry; z: (n,) or (N, n) likewise; P: (n, q) shared basis or None.
     Returns device tensors (values[N], grads[N, 1+noise+d], info[N]); gradient rows of entries that are not
     positive definite are zeroed (torch_backend.py:528-529)."""
+    theta, x, z, P, iso = _batched_operands(theta, x, z, P, noise)
     N = theta.shape[0]
     per_entry_x = x.dim() == 3
     n, d = x.shape[-2], x.shape[-1]
@@ -699,20 +734,24 @@ def criterion_batched_grad(theta, x, z, P, p, noise=False, max_bytes=None, work=
     per_entry_z = z.dim() == 2
     if per_entry_z and z.shape[0] != N:
         raise _abi.GpmpError(f"z has {z.shape[0]} rows for {N} parameter rows")
+    if z.shape[-1] != n:
+        raise _abi.GpmpError(f"z has {z.shape[-1]} observations for {n} points")
     q = 0 if P is None else P.shape[1]
     spec = _abi.make_spec(p, d, 0.0, [0.0] * d, noise=noise)
-    width = 1 + int(bool(noise)) + d
+    head = 1 + int(bool(noise))
+    width = head + d
     values, grads = _empty((N,)), _empty((N, width))
     info = torch.empty(max(N, 1), dtype=torch.int32, device=device())
     if N == 0:
-        return values, grads, info[:0]
-    x, z = x.contiguous(), z.contiguous()
+        return values, grads[:, : head + 1] if iso else grads, info[:0]
     if work is None:
         work = criterion_batched_grad_workspace(n, q, d, N, max_bytes)
-    check(lib().gpmp_criterion_batched_grad(C.byref(spec), ptr(theta.contiguous()), N, ptr(x),
+    check(lib().gpmp_criterion_batched_grad(C.byref(spec), ptr(theta), N, ptr(x),
                                             n * d if per_entry_x else 0, n, ptr(z), n if per_entry_z else 0,
                                             ptr(P), q, ptr(work), work.numel(), ptr(values), ptr(grads), ptr(info),
                                             stream_ptr()), "gpmp_criterion_batched_grad")
     info = info[:N]
     grads = torch.where((info != 0).reshape(-1, 1), torch.zeros_like(grads), grads)
+    if iso:  # one length-scale parameter: its gradient is the sum over the d expanded columns
+        grads = torch.cat((grads[:, :head], grads[:, head:].sum(dim=1, keepdim=True)), dim=1)
     return values, grads, info

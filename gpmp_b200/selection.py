@@ -1,21 +1,19 @@
-"""Host-side parameter selection around the device criterion: the caller of the hot path.
+"""Initial guesses for the covariance parameters (gpmp/kernel/init.py:24-66): each is ONE
+hot-path call (a GLS variance at length-scales taken from the data range), so it lives with the device code.
 
-GPmp drives the inner loop from `gpmp/kernel/parameter_selection.py` (SciPy SLSQP / L-BFGS-B over a criterion
-closure, :35-437, :583-1577) and seeds it with `gpmp/kernel/init.py:24-66`.  Those modules are plain host control
-flow and can be used unchanged on top of `gpmp_b200.num` / `gpmp_b200.core`; this file restates the small part of
-them that the BASELINE configs exercise (array data, ML / REML, optional parameterised mean) so that the
-package is usable on its own: same function names, argument order, defaults and the same info fields.
-Dataloader / mini-batch selection, priors (REMAP) and custom bounds helpers are not restated.
+The optimiser loop itself (`autoselect_parameters`, `select_parameters_with_*`, gpmp/kernel/parameter_selection.py)
+is host control flow that is out of scope here: GPmp's own driver runs unchanged on top of this library once
+`gpmp_b200.dropin.install()` has bound the model / kernel seams (tests/test_dropin_gpu.py runs its REML and REMAP
+selections that way).  `multistart_reml` below is the one front-end this package adds: the restarts of a
+multi-start selection evaluated as ONE batched value+gradient sweep per optimiser iteration.
 """
 from __future__ import annotations
 
 import math
-import time
 
 import numpy as np
-from scipy.optimize import OptimizeResult, minimize
 
-from . import num, ops
+from . import ops
 
 
 # ---- criteria (kernel/parameter_selection.py:560-581) --------------------------------------------------------
@@ -66,137 +64,86 @@ def anisotropic_parameters_initial_guess(model, xi, zi):
     return _covparam(sigma2, rho)
 
 
-# ---- criterion closures (kernel/parameter_selection.py:35-124) --------------------------------------------------
-def make_selection_criterion_with_gradient(model, selection_criterion, xi, zi, parameterized_mean=False,
-                                           meanparam_len=1):
-    if parameterized_mean:
-        def crit_(param, x, z):
-            return selection_criterion(model, param[:meanparam_len], param[meanparam_len:], x, z)
-    else:
-        def crit_(covparam, x, z):
-            return selection_criterion(model, covparam, x, z)
-    crit = num.DifferentiableSelectionCriterion(crit_, xi, zi)
-    return crit.evaluate, crit.evaluate_pre_grad, crit.evaluate_no_grad, crit.gradient
+# ---- multi-start selection on the batched value+gradient sweep -------------------------------
+def multistart_reml(model, xi, zi, p, starts, kind="reml", max_iter=200, gtol=1e-5, ftol=1e-9, group=None):
+    """Minimise the REML (or zero-mean ML) criterion from every row of `starts` (R x (1+d)) at once.
 
+    GPmp restarts `autoselect_parameters` (kernel/parameter_selection.py:128-276) one start at a time, each
+    iteration one value + gradient on the same (xi, zi).  Here every iteration evaluates all R current points in
+    one `BatchedCriterion.value_and_grad` sweep (C-ABI gpmp_criterion_batched_grad; rows shard over the ranks of
+    `group`), and each restart advances by its own L-BFGS direction (memory 8) with Armijo backtracking, also
+    batched: the trial points of all restarts that still search form the next sweep.  Box: +-10 around each start,
+    like the reference's automatic bounds.  Returns (best_theta, best_value, info) with the per-restart end
+    points, values, iteration counts and the number of sweeps."""
+    from . import batched
 
-# ---- optimiser driver (kernel/parameter_selection.py:128-276) ----------------------------------------------------
-def autoselect_parameters(p0, criterion, gradient, bounds=None, bounds_auto=True, bounds_delta=10.0, silent=True,
-                          info=False, method="SLSQP", method_options=None):
-    tic = time.time()
-    p0 = np.asarray(num.to_np(p0), dtype=np.float64)
-    if bounds is None and bounds_auto:
-        bounds = [(max(v - bounds_delta, -500.0), min(v + bounds_delta, 500.0)) for v in p0]
-    hist_p, hist_j = [], []
-    best = {"J": float("inf"), "p": None}
+    crit = batched.BatchedCriterion(model, xi, zi, p, kind=kind, group=group)
+    X = np.array(starts, dtype=np.float64, copy=True)
+    if X.ndim == 1:
+        X = X.reshape(1, -1)
+    R, dim = X.shape
+    lo, hi = X - 10.0, X + 10.0
+    F, G = crit.value_and_grad(X)
+    sweeps = 1
+    F = np.where(np.isfinite(F), F, np.inf)
+    S = [[] for _ in range(R)]  # (s, y) pairs per restart
+    active = np.isfinite(F)
+    iters = np.zeros(R, dtype=int)
 
-    def fun(p):
-        try:
-            J = criterion(p)
-        except Exception as exc:  # noqa: BLE001 - linear-algebra failures count as +inf, like the reference
-            if num._is_linalg_exception(exc):
-                J = np.inf
-            else:
-                raise
-        J = float(J)
-        hist_p.append(p.copy())
-        hist_j.append(J)
-        if J < best["J"]:
-            best["J"], best["p"] = J, p.copy()
-        return J
+    def direction(r):
+        q = G[r].copy()
+        alphas = []
+        for s, y in reversed(S[r]):
+            a = s.dot(q) / y.dot(s)
+            alphas.append(a)
+            q -= a * y
+        if S[r]:
+            s, y = S[r][-1]
+            q *= s.dot(y) / y.dot(y)
+        else:
+            q /= max(1.0, np.linalg.norm(q))
+        for (s, y), a in zip(S[r], reversed(alphas)):
+            q += (a - y.dot(q) / y.dot(s)) * s
+        return -q
 
-    def jac(p):
-        return np.asarray(num.to_np(gradient(p)), dtype=np.float64)
-
-    options = {"disp": not silent}
-    if method == "L-BFGS-B":
-        # the reference also passes disp / iprint=-1 (parameter_selection.py:236-247); current SciPy has dropped
-        # both for this solver and only warns about them, so they are left out
-        options = dict(maxcor=20, ftol=1e-6, gtol=1e-5, eps=1e-8, maxfun=15000, maxiter=15000, maxls=40)
-    elif method == "SLSQP":
-        options.update(dict(ftol=1e-6, eps=1e-8, maxiter=15000))
-    else:
-        raise ValueError("Optimization method not implemented.")
-    options.update(method_options or {})
-    r = minimize(fun, p0, method=method, jac=jac, bounds=bounds, options=options)
-    best_p = best["p"] if best["p"] is not None else r.x
-    if info:
-        r = OptimizeResult(r)
-        r["history_params"] = hist_p
-        r["history_criterion"] = hist_j
-        r["initial_params"] = p0
-        r["final_params"] = best_p
-        r["bounds"] = bounds
-        r["selection_criterion"] = criterion
-        r["total_time"] = time.time() - tic
-        return best_p, r
-    return best_p, None
-
-
-# ---- front-ends (kernel/parameter_selection.py:280-437, 583-800) ---------------------------------------------------
-def select_parameters_with_criterion(model, criterion, xi=None, zi=None, meanparam0=None, covparam0=None,
-                                     parameterized_mean=False, meanparam_len=1, info=False, verbosity=0, *,
-                                     bounds=None, bounds_auto=True, bounds_delta=10.0, method="SLSQP",
-                                     method_options=None):
-    tic = time.time()
-    if covparam0 is None:
-        covparam0 = anisotropic_parameters_initial_guess(model, xi, zi)
-    covparam0 = np.asarray(num.to_np(covparam0), dtype=np.float64)
-    if parameterized_mean:
-        if meanparam0 is None:
-            raise ValueError("meanparam0 must be provided when parameterized_mean=True.")
-        param0 = np.concatenate((np.asarray(num.to_np(meanparam0), dtype=np.float64).reshape(-1), covparam0))
-    else:
-        param0 = covparam0
-    crit, crit_pre_grad, crit_no_grad, crit_grad = make_selection_criterion_with_gradient(
-        model, criterion, xi, zi, parameterized_mean=parameterized_mean, meanparam_len=meanparam_len)
-    if verbosity == 1:
-        print("Parameter selection using custom criterion...")
-    param_opt, info_ret = autoselect_parameters(param0, crit_pre_grad, crit_grad, bounds=bounds,
-                                                bounds_auto=bounds_auto, bounds_delta=bounds_delta,
-                                                silent=verbosity != 2, info=True, method=method,
-                                                method_options=method_options)
-    if verbosity == 1:
-        print("done.")
-    if parameterized_mean:
-        meanparam_opt, covparam_opt = param_opt[:meanparam_len], param_opt[meanparam_len:]
-        model.meanparam = num.asparam(meanparam_opt)
-    else:
-        meanparam_opt, covparam_opt = None, param_opt
-    model.covparam = num.asparam(covparam_opt)
-    if info:
-        info_ret["meanparam0"] = meanparam0 if parameterized_mean else None
-        info_ret["covparam0"] = covparam0
-        info_ret["meanparam"] = meanparam_opt
-        info_ret["covparam"] = covparam_opt
-        info_ret["selection_criterion"] = crit
-        info_ret["selection_criterion_nograd"] = crit_no_grad
-        info_ret["time"] = time.time() - tic
-        return model, info_ret
-    return model, None
-
-
-def select_parameters_with_reml(model, xi=None, zi=None, covparam0=None, info=False, verbosity=0, **kwargs):
-    """REML selection of the covariance parameters (kernel/parameter_selection.py:730-800)."""
-    return select_parameters_with_criterion(model, negative_log_restricted_likelihood, xi=xi, zi=zi,
-                                            covparam0=covparam0, info=info, verbosity=verbosity, **kwargs)
-
-
-def select_parameters_with_ml_zero_mean(model, xi=None, zi=None, covparam0=None, info=False, verbosity=0, **kwargs):
-    """Maximum likelihood for a zero-mean model."""
-    if covparam0 is None:
-        covparam0 = anisotropic_parameters_initial_guess_zero_mean(model, xi, zi)
-    return select_parameters_with_criterion(model, negative_log_likelihood_zero_mean, xi=xi, zi=zi,
-                                            covparam0=covparam0, info=info, verbosity=verbosity, **kwargs)
-
-
-def select_parameters_with_ml(model, xi=None, zi=None, meanparam0=None, covparam0=None, info=False, verbosity=0,
-                              **kwargs):
-    """Maximum likelihood with a parameterised mean: the optimisation vector is [meanparam, covparam]."""
-    if covparam0 is None or meanparam0 is None:
-        m0, c0 = anisotropic_parameters_initial_guess_constant_mean(model, xi, zi)
-        meanparam0 = m0 if meanparam0 is None else meanparam0
-        covparam0 = c0 if covparam0 is None else covparam0
-    meanparam0 = np.asarray(num.to_np(meanparam0), dtype=np.float64).reshape(-1)
-    return select_parameters_with_criterion(model, negative_log_likelihood, xi=xi, zi=zi, meanparam0=meanparam0,
-                                            covparam0=covparam0, parameterized_mean=True,
-                                            meanparam_len=len(meanparam0), info=info, verbosity=verbosity, **kwargs)
+    for _ in range(max_iter):
+        idx = np.flatnonzero(active)
+        if idx.size == 0:
+            break
+        Dm = np.array([direction(r) for r in idx])
+        slope = np.einsum("ij,ij->i", Dm, G[idx])
+        bad = slope >= 0.0  # not a descent direction: fall back to steepest descent and forget the memory
+        for k in np.flatnonzero(bad):
+            S[idx[k]] = []
+            Dm[k] = -G[idx[k]] / max(1.0, np.linalg.norm(G[idx[k]]))
+        slope = np.einsum("ij,ij->i", Dm, G[idx])
+        step = np.ones(idx.size)
+        searching = np.ones(idx.size, dtype=bool)
+        Xn, Fn, Gn = X[idx].copy(), F[idx].copy(), G[idx].copy()
+        for _ls in range(25):
+            k = np.flatnonzero(searching)
+            if k.size == 0:
+                break
+            T = np.clip(X[idx[k]] + step[k, None] * Dm[k], lo[idx[k]], hi[idx[k]])
+            Ft, Gt = crit.value_and_grad(T)
+            sweeps += 1
+            ok = np.isfinite(Ft) & (Ft <= F[idx[k]] + 1e-4 * step[k] * slope[k])
+            for j in np.flatnonzero(ok):
+                Xn[k[j]], Fn[k[j]], Gn[k[j]] = T[j], Ft[j], Gt[j]
+            searching[k[ok]] = False
+            step[k[~ok]] *= 0.5
+        for k, r in enumerate(idx):
+            iters[r] += 1
+            if searching[k]:  # no acceptable step: this restart has converged as far as it can
+                active[r] = False
+                continue
+            s, y = Xn[k] - X[r], Gn[k] - G[r]
+            if s.dot(y) > 1e-12 * np.linalg.norm(s) * np.linalg.norm(y):
+                S[r] = (S[r] + [(s, y)])[-8:]
+            small = abs(F[r] - Fn[k]) <= ftol * max(1.0, abs(Fn[k])) or np.max(np.abs(Gn[k])) <= gtol
+            X[r], F[r], G[r] = Xn[k], Fn[k], Gn[k]
+            if small:
+                active[r] = False
+    best = int(np.argmin(F))
+    info = {"thetas": X, "values": F, "iterations": iters, "sweeps": sweeps, "best_index": best}
+    return X[best].copy(), float(F[best]), info

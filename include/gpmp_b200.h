@@ -61,9 +61,15 @@ unsigned long long gpmp_launch_count(void);
 /* Per-class CUDA-event profiling (classes: 0 covariance build, 1 DMMA GEMM, 2 panel factor,
  * 3 dK contraction, 4 small/reduction, 5 batched criterion).  enable!=0 brackets each launch with
  * events on its stream; gpmp_prof_read synchronises those events and returns accumulated
- * milliseconds, launches and algorithmic work (flops or bytes), then clears the class. */
+ * milliseconds, launches and algorithmic work (flops or bytes), then clears the class.  enable == 2
+ * additionally issues the look-ahead streams' launches on the caller's stream (same kernels, serialised), so
+ * the class times are exclusive kernel times. */
 int gpmp_prof_enable(int enable);
 int gpmp_prof_read(int kernel_class, double* ms, unsigned long long* launches, double* work);
+/* FP64 tensor-pipe probe for the roofline denominator (MEASURED_PEAKS.json carries no
+ * FP64 entry): `ctas` CTAs of 16 warps issue `iters` rounds of 8 independent DMMA.8x8x4 from registers;
+ * *flops_out receives the flops enqueued (2*8*8*4 per DMMA).  The caller times the launch with CUDA events. */
+int gpmp_measure_dmma_peak(int ctas, int iters, double* sink_dev, double* flops_out, void* stream);
 
 /* ---- L0/L1: distances and Matern covariance --------------------------------------------------
  * replaces gnp.scaled_distance (gpmp/num/torch_backend.py:810-820, numpy_backend.py:432-436):

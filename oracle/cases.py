@@ -101,3 +101,69 @@ def headline(n=8192, d=8, seed=1234):
     x, z, _ = data(n, d, seed)
     th0 = np.concatenate(([0.0], np.full(d, -np.log(0.7))))
     return x, z, th0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Benchmarked-size cases (BASELINE.json configs 1-5): inputs for oracle/make_golden_large.py and the GPU tests
+# ---------------------------------------------------------------------------------------------------------
+_H6_ALPHA = np.array([1.0, 1.2, 3.0, 3.2])
+_H6_A = np.array([[10, 3, 17, 3.5, 1.7, 8], [0.05, 10, 17, 0.1, 8, 14], [3, 3.5, 1.7, 10, 17, 8],
+                  [17, 8, 0.05, 10, 0.1, 14]], dtype=np.float64)
+_H6_P = 1e-4 * np.array([[1312, 1696, 5569, 124, 8283, 5886], [2329, 4135, 8307, 3736, 1004, 9991],
+                         [2348, 1451, 3522, 2883, 3047, 6650], [4047, 8828, 8732, 5743, 1091, 381]],
+                        dtype=np.float64)
+
+
+def hartmann6(x):
+    """The 6-d Hartmann test function (public definition), the response of BASELINE config 2."""
+    d2 = ((x[:, None, :] - _H6_P[None, :, :]) ** 2 * _H6_A[None, :, :]).sum(axis=2)
+    return -(np.exp(-d2) * _H6_ALPHA[None, :]).sum(axis=1)
+
+
+def large_cfg2(n=2000, d=6, seed=2002):
+    """config 2: x ~ U[0,1]^{2000x6}, z = hartmann6(x) + 0.1 N(0,1); theta = [log s2, log tau2, log 1/rho_1..6]."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(size=(n, d))
+    z = hartmann6(x) + 0.1 * rng.standard_normal(n)
+    th = np.concatenate(([np.log(0.2), np.log(0.01)], -np.log(0.6) + 0.2 * rng.standard_normal(d)))
+    return x, z, th
+
+
+def large_cfg4(n=512, d=4, N=256, seed=4004):
+    """config 4: x ~ U[0,1]^{512x4}, z = sin(3 sum x) + 0.1 N; particles theta_hat + U(-2, 2)^{N x 5}."""
+    x, z, _ = data(n, d, seed)
+    th_hat = theta(d, seed)
+    TH = th_hat + np.random.default_rng(seed + 3).uniform(-2.0, 2.0, size=(N, d + 1))
+    return x, z, TH
+
+
+def large_cfg5(n=4096, d=10, m=4096, paths=4, seed=5005):
+    """config 5 shape at the size where the reference's dense predictor still fits: predict + conditioning."""
+    x, z, xt = data(n, d, seed, m)
+    th = theta(d, seed)
+    ztsim = np.random.default_rng(seed + 7).standard_normal((n + m, paths))
+    return x, z, xt, th, ztsim
+
+
+def large_cfg3_theta(d=8, seed=3003):
+    """A second headline-size parameter vector (theta0 + U(-0.25, 0.25)), as bench.py draws them."""
+    th0 = np.concatenate(([0.0], np.full(d, -np.log(0.7))))
+    return th0 + np.random.default_rng(seed).uniform(-0.25, 0.25, size=th0.shape)
+
+
+def example02():
+    """config 1 (examples/gpmp_example02_1d_interpolation.py shape): the 6 points / 200 test points / p stored with
+    the REML golden run of oracle/make_golden.py."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                             "reference_torch.npz"))
+    pre = "select_reml_example02/"
+    return g[pre + "x"], g[pre + "z"], g[pre + "xt"], int(g[pre + "p"])
+
+
+def smc_small(n=40, d=2, seed=6006):
+    """A small model for a complete tempered SMC run: data and the sampling box theta_hat +- 3."""
+    x, z, _ = data(n, d, seed)
+    th = theta(d, seed)
+    return x, z, [list(th - 3.0), list(th + 3.0)]

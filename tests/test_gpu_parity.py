@@ -284,14 +284,10 @@ def test_reml_selection_example02_end_to_end(gp, golden_t):
     assert r.success
     assert abs(best["J"] - float(g["fun"])) <= 1e-6 * max(1.0, abs(float(g["fun"])))
     assert np.max(np.abs(best["p"] - g["covparam"])) <= 1e-3
-    # the packaged driver (initial guess + SLSQP) must retrace the reference's run: same start, same optimum
-    m2 = gp.core.Model(cases.mean_fn("const", gp.num),
-                       lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, p, cp, pairwise))
-    m2, info = gp.kernel.select_parameters_with_reml(m2, x, z, info=True)
-    assert np.max(np.abs(info["covparam0"] - th0)) <= 1e-8 * max(1.0, np.max(np.abs(th0)))
-    assert abs(float(info.fun) - float(g["fun"])) <= 1e-6 * max(1.0, abs(float(g["fun"])))
-    assert np.max(np.abs(np.asarray(m2.covparam) - g["covparam"])) <= 1e-3
-    assert callable(info["selection_criterion_nograd"]) and np.isfinite(float(info.selection_criterion_nograd(g["covparam"])))
+    # the initial guess (kernel/init.py:54-66, one hot-path call) reproduces the reference's starting point; GPmp's
+    # own driver on top of this library is exercised in tests/test_dropin_gpu.py
+    th_init = gp.kernel.anisotropic_parameters_initial_guess(m, gp.num.asarray(x), gp.num.asarray(z))
+    assert np.max(np.abs(th_init - th0)) <= 1e-8 * max(1.0, np.max(np.abs(th0)))
     m.covparam = g["covparam"]  # predict at the reference's parameters: isolates the predictor from the optimiser
     mean, var = m.predict(x, z, xt)
     s2 = float(np.exp(g["covparam"][0]))
@@ -414,6 +410,56 @@ def test_batched_extra_rows_variants(gp, kind, mean, d):
         else:
             v = m.negative_log_restricted_likelihood(TH[i], x, z).item()
         assert relerr(vals[i], v) <= 1e-11, (i, vals[i], v)
+
+
+@pytest.mark.parametrize("n,mean,d,N", [(1100, "const", 3, 1), (1100, "zero", 3, 3), (2048, "const", 4, 1),
+                                          (2048, "linear", 8, 3), (1500, "const", 6, 4)])
+def test_batched_large_n_matches_scalar(gp, n, mean, d, N):
+    """Batched sweeps beyond one column group (n > 1024: NB > 128, in-group K=128 updates combined with the
+    extra-row strip, block inverses with batch > 1), with ONE particle (the MH loop: must not take the single-matrix
+    look-ahead path, whose block-diagonal inverses need ceil(n/128) tiles) and with workspaces that force
+    cap = 1 and cap = N - 1 particles in flight: every value equals the scalar fused path."""
+    x, z, _ = cases.data(n, d, 300 + n)
+    th0 = cases.theta(d, 300 + n)
+    TH = th0 + np.random.default_rng(n + N).uniform(-0.5, 0.5, size=(N, d + 1))
+    m = _model(gp, mean, 2, False, th0)
+    kind = "ml" if mean == "zero" else "reml"
+    f = m.negative_log_likelihood_zero_mean if mean == "zero" else m.negative_log_restricted_likelihood
+    ref = np.array([f(TH[i], x, z).item() for i in range(N)])
+    q = {"zero": 0, "const": 1, "linear": d + 1}[mean]
+    per1 = gp._abi.lib().gpmp_criterion_batched_bytes(n, q, 1)
+    per = gp._abi.lib().gpmp_criterion_batched_bytes(n, q, 2) - per1
+    budgets = [None, per1] + ([per1 + (N - 2) * per] if N > 2 else [])
+    for mb in budgets:
+        vals = gp.batched.BatchedCriterion(m, x, z, 2, kind=kind, max_bytes=mb)(TH)
+        assert relerr(vals, ref) <= 1e-10, (mb, vals, ref)
+    if N > 1 and mean != "zero":
+        v2, g2 = gp.batched.BatchedCriterion(m, x, z, 2, kind=kind).value_and_grad(TH[:2])
+        for i in range(2):
+            v, gi = gp.num.value_and_grad(lambda t: f(t, x, z), TH[i])
+            assert relerr(v2[i], float(v)) <= 1e-9 and relerr_norm(g2[i], gi.cpu().numpy()) <= 1e-8
+
+
+def test_batched_operand_validation(gp):
+    """theta width / rank / device are checked before anything reaches the C side; an isotropic parameter row
+    is expanded (and its gradient folded back) like the scalar path does."""
+    n, d = 96, 3
+    x, z, _ = cases.data(n, d, 5)
+    th0 = cases.theta(d, 5)
+    m = _model(gp, "const", 2, False, th0)
+    crit = gp.batched.BatchedCriterion(m, x, z, 2)
+    with pytest.raises(gp._abi.GpmpError):
+        crit(np.zeros((4, d + 3)))
+    iso = np.array([[0.1, 0.3], [-0.2, 0.5]])
+    full = np.concatenate((iso[:, :1], np.repeat(iso[:, 1:], d, axis=1)), axis=1)
+    assert np.array_equal(crit(iso), crit(full))
+    vi, gi = crit.value_and_grad(iso)
+    vf, gf = crit.value_and_grad(full)
+    assert gi.shape == (2, 2) and relerr(vi, vf) == 0.0
+    assert relerr_norm(gi[:, 1], gf[:, 1:].sum(axis=1)) <= 1e-13
+    # CPU / non-contiguous tensors are moved and packed, not handed over as they are
+    tht = torch.as_tensor(np.asfortranarray(full))
+    assert np.array_equal(crit(tht), crit(full))
 
 
 def _mb_golden():

@@ -72,13 +72,17 @@ def test_bench_inputs_are_the_seeded_headline_case():
 
 
 def test_bench_reference_arm_prints_contract_line():
-    env = dict(os.environ, OMP_NUM_THREADS="4")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0", "--ref-n", "1024"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    from oracle import vendor_ref
+
+    assert line["cpu_baseline"]["kind"] == ("reference" if vendor_ref.available() else "port")
+    assert line["cpu_baseline"]["cores"] == os.cpu_count()  # torchrun's OMP_NUM_THREADS=1 must not bite
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["metric"] == "REML logL+grad evals/s (n=8192,d=8,fp64)"
 
 
@@ -90,56 +94,77 @@ def test_build_entry_point():
     assert os.path.exists(os.path.join(ROOT, "gpmp_b200", "libgpmp_b200.so"))
 
 
-# ---- host-side selection driver (gpmp_b200/selection.py; mirrors kernel/parameter_selection.py:128-276) ----------
-def test_autoselect_parameters_driver_on_a_quadratic():
-    """The SciPy loop around a criterion: bounds, history, best-seen tracking and the info fields the samplers
-    read -- exercised on a closed-form criterion (no device needed)."""
-    from gpmp_b200 import selection
+# ---- drop-in binding (gpmp_b200/dropin.py) against the vendored reference, host logic only --------------------------
+def test_dropin_install_patches_and_restores_the_reference():
+    from oracle import vendor_ref
 
-    target = np.array([0.5, -1.5, 2.0])
+    if not vendor_ref.available() and not vendor_ref.vendor():
+        pytest.skip("no reference tree here")
+    gp = vendor_ref.import_reference("torch")
+    import gpmp.core.model as model_mod
+    import gpmp.kernel.matern as matern
+    import gpmp.mcmc.param_posterior as post
+    import gpmp.num as gnp
+    from gpmp_b200 import dropin, kernel
 
-    def crit(p):
-        return float(np.sum((np.asarray(p) - target) ** 2) + 3.0)
-
-    def grad(p):
-        return 2.0 * (np.asarray(p) - target)
-
-    p0 = np.zeros(3)
-    for method in ("SLSQP", "L-BFGS-B"):
-        best, info = selection.autoselect_parameters(p0, crit, grad, info=True, method=method)
-        assert np.allclose(best, target, atol=1e-4) and abs(info.fun - 3.0) <= 1e-6
-        assert len(info["history_params"]) == len(info["history_criterion"]) >= 2
-        assert np.array_equal(info["initial_params"], p0) and np.allclose(info["final_params"], best)
-        assert info["bounds"] == [(-10.0, 10.0)] * 3 and info["total_time"] >= 0.0
-    # explicit bounds are honoured; automatic bounds are clipped to +-500
-    best, _ = selection.autoselect_parameters(p0, crit, grad, bounds=[(-1, 0.2), (-1, 1), (0, 1)])
-    assert np.allclose(best, [0.2, -1.0, 1.0], atol=1e-6)
-    _, info = selection.autoselect_parameters(np.array([495.0]), lambda p: float((p[0] - 490.0) ** 2),
-                                              lambda p: 2.0 * (np.asarray(p) - 490.0), info=True)
-    assert info["bounds"] == [(485.0, 500.0)]
-    with pytest.raises(ValueError):
-        selection.autoselect_parameters(p0, crit, grad, method="Nelder-Mead")
+    before = (model_mod.Model.predict, matern.maternp_covariance, gnp.scaled_distance, post.run_smc_sampling)
+    dropin.install(gp)
+    try:
+        assert gp.kernel.maternp_covariance is kernel.maternp_covariance
+        assert matern.maternp_covariance is kernel.maternp_covariance
+        assert model_mod.Model.negative_log_restricted_likelihood.__name__ == "negative_log_restricted_likelihood"
+        assert model_mod.Model.predict is not before[0] and post.run_smc_sampling is not before[3]
+        dropin.install(gp)  # idempotent
+    finally:
+        dropin.uninstall()
+    after = (model_mod.Model.predict, matern.maternp_covariance, gnp.scaled_distance, post.run_smc_sampling)
+    assert after == before
 
 
-def test_autoselect_parameters_maps_linear_algebra_failures_to_inf():
-    """A criterion that raises a linear-algebra error on part of the domain counts as +inf there
-    (parameter_selection.py:222-231); any other exception propagates."""
-    from gpmp_b200 import selection
+def test_dropin_smc_uses_the_batched_sweep():
+    """The reference's sample_from_selection_criterion_smc (param_posterior.py:658-775) with a BatchableCriterion:
+    the wrapper around run_smc_sampling must find the criterion and the box inside the sampler's `logpdf_temp`
+    closure and replace the per-particle loop; the target here is a closed-form quadratic (no device)."""
+    from oracle import vendor_ref
 
-    def crit(p):
-        if p[0] > 1.0:
-            raise torch.linalg.LinAlgError("not positive definite")
-        return float((p[0] - 0.9) ** 2)
+    if not vendor_ref.available() and not vendor_ref.vendor():
+        pytest.skip("no reference tree here")
+    gp = vendor_ref.import_reference("torch")
+    import gpmp.num as gnp
+    from gpmp_b200 import dropin
 
-    best, info = selection.autoselect_parameters(np.array([0.0]), crit, lambda p: 2.0 * (np.asarray(p) - 0.9),
-                                                 info=True)
-    assert abs(best[0] - 0.9) <= 1e-3 and np.isfinite(info["history_criterion"]).any()
+    centre = np.array([0.5, -1.0])
 
-    def broken(p):
-        raise KeyError("unrelated")
+    class Quad(dropin.BatchableCriterion):
+        def __init__(self):
+            self.sweeps, self.evaluations, self.scalar_calls, self.extra_term = 0, 0, 0, None
 
-    with pytest.raises(KeyError):
-        selection.autoselect_parameters(np.array([0.0]), broken, lambda p: np.zeros(1))
+        def batched(self, thetas):
+            th = np.asarray(thetas, dtype=np.float64).reshape(-1, 2)
+            self.sweeps += 1
+            self.evaluations += th.shape[0]
+            return 0.5 * np.sum(((th - centre) / 0.3) ** 2, axis=1)
+
+        def __call__(self, theta):
+            self.scalar_calls += 1
+            return float(self.batched(theta)[0])
+
+    crit = Quad()
+    box = [[-3.0, -4.0], [3.0, 3.0]]
+    dropin.install(gp)
+    try:
+        particles, smc = gp.mcmc.sample_from_selection_criterion_smc(
+            selection_criterion=crit, init_box=box, sampling_box=box, n_particles=300, mh_steps=5)
+    finally:
+        dropin.uninstall()
+    P = gnp.to_np(particles)
+    assert crit.scalar_calls == 0 and crit.sweeps > 5 and crit.evaluations > 300 * 5
+    assert np.all(np.abs(P.mean(axis=0) - centre) <= 0.1) and np.all(np.abs(P.std(axis=0) - 0.3) <= 0.1)
+    # the same call without the binding walks the particles one by one
+    crit2 = Quad()
+    gp.mcmc.sample_from_selection_criterion_smc(selection_criterion=crit2, init_box=box, sampling_box=box,
+                                                n_particles=50, mh_steps=2)
+    assert crit2.scalar_calls > 50
 
 
 # ---- mini-batch criterion: host logic (grouping by batch size, reductions, cycling) without a device ----------
