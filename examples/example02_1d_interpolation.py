@@ -1,33 +1,47 @@
-"""BASELINE config 1 with gpmp_b200: 1-D interpolation, Matern p=3, constant mean, REML selection, prediction
-at 200 points (the scenario of GPmp's examples/gpmp_example02_1d_interpolation.py, without the plots)."""
+"""BASELINE config 1: GPmp's examples/gpmp_example02_1d_interpolation.py scenario (without the plots) with the
+B200 hot path bound into GPmp itself: the model, the REML / REMAP selection drivers and the priors are GPmp's own
+code; `gpmp_b200.dropin.install()` routes the kernel / Model seams to the CUDA kernels.
+
+    GPMP_BACKEND=torch python examples/example02_1d_interpolation.py      # needs GPmp importable as `gpmp`
+"""
+import os
+
+os.environ.setdefault("GPMP_BACKEND", "torch")
 import numpy as np
 
-import gpmp_b200 as gp
+try:
+    import gpmp as gp
+except ImportError:  # in this repository GPmp lives under oracle/_ref (test infrastructure, not shipped)
+    import sys
 
-gnp = gp.num
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import vendor_ref
 
+    gp = vendor_ref.import_reference("torch")
+import gpmp.num as gnp
 
-def twobumps(x):
-    # gpmp/misc/testfunctions.py: two Gaussian bumps on [-1, 1]
-    x = np.asarray(x).reshape(-1)
-    return 0.7 * np.exp(-((x + 0.4) ** 2) / 0.02) + np.exp(-((x - 0.3) ** 2) / 0.05)
+import gpmp_b200.dropin as b200
 
 
 def main():
+    b200.install(gp)
     rng = np.random.default_rng(1234)
     xi = np.sort(rng.uniform(-1.0, 1.0, size=(6, 1)), axis=0)
-    zi = twobumps(xi)
+    zi = gp.misc.testfunctions.twobumps(xi)
     xt = np.linspace(-1.0, 1.0, 200).reshape(-1, 1)
     p = 3
-    model = gp.core.Model(lambda x, meanparam: gnp.ones((x.shape[0], 1)),
-                          lambda x, y, covparam, pairwise=False: gp.kernel.maternp_covariance(x, y, p, covparam, pairwise))
-    model, info = gp.kernel.select_parameters_with_reml(model, xi, zi, info=True)
-    zpm, zpv = model.predict(xi, zi, xt)
-    print("covparam0 :", info["covparam0"])
-    print("covparam  :", np.asarray(model.covparam), " criterion:", float(info.fun), " iterations:", info.nit)
-    print("max |error| on the grid:", float(np.max(np.abs(zpm - twobumps(xt)))),
-          " max predictive sd:", float(np.sqrt(zpv.max())))
-    zloo, s2loo, eloo = model.loo(xi, zi, convert_out=True)
+
+    def model():
+        return gp.core.Model(lambda x, meanparam: gnp.ones((x.shape[0], 1)),
+                             lambda x, y, covparam, pairwise=False: gp.kernel.maternp_covariance(x, y, p, covparam, pairwise))
+
+    for name, select in (("REML", gp.kernel.select_parameters_with_reml), ("REMAP", gp.kernel.select_parameters_with_remap)):
+        m, info = select(model(), xi, zi, info=True)
+        zpm, zpv = m.predict(xi, zi, xt)
+        print(f"{name}: covparam {gnp.to_np(m.covparam)}  criterion {float(info.fun):.6f}  iterations {info.nit}")
+        print(f"      max |error| on the grid {float(np.max(np.abs(zpm - gp.misc.testfunctions.twobumps(xt)))):.4f}"
+              f"  max predictive sd {float(np.sqrt(zpv.max())):.4f}")
+    zloo, s2loo, eloo = m.loo(xi, zi, convert_out=True)
     print("LOO errors:", eloo)
 
 

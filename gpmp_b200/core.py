@@ -249,10 +249,38 @@ class Model:
         return self.fit(xi, zi).predict(xt, return_lambdas=return_lambdas, zero_neg_variances=zero_neg_variances,
                                         convert_out=convert_out)
 
+    # ------------------------------------------------------------------ kriging predictors (core/model.py:196-222)
+    def kriging_predictor_with_zero_mean(self, xi, xt, return_type=0):
+        """(lambda_t, posterior variance) of simple kriging (core/kriging.py:35-67); return_type -1: no variance,
+        0: marginal variances (m,), 1: the full posterior covariance (m, m).  Device tensors."""
+        return self._kriging(xi, xt, None, return_type)
+
+    def kriging_predictor(self, xi, xt, return_type=0):
+        """(lambda_t, posterior variance) of universal kriging with the basis mean(x, .) (core/kriging.py:70-116,
+        by block elimination instead of the (n+q) saddle system)."""
+        xi_ = ops.to_device(xi)
+        return self._kriging(xi_, xt, self._basis(xi_), return_type)
+
+    def _kriging(self, xi, xt, P, return_type):
+        if return_type not in (-1, 0, 1):
+            raise ValueError("return_type must be in {-1, 0, 1}")
+        xi_, _, xt_ = _ensure_shapes_and_type(xi=xi, xt=xt)
+        covparam = _as_param(self.covparam)
+        with torch.no_grad():
+            zero = torch.zeros(xi_.shape[0], dtype=torch.float64, device=xi_.device)
+            state, out = self._fit(xi_, zero, P, covparam)
+            if ops.read_small(out)[6] != 0.0:
+                raise torch.linalg.LinAlgError("kriging_predictor: K(xi, xi) is not positive-definite")
+        fitted = Fitted(self, state, xi_, zero, covparam)
+        return fitted.weights_and_variance(xt_, return_type)
+
     # ------------------------------------------------------------------ sample paths
     def sample_paths(self, xt, nb_paths, method="chol", check_result=True):
         """nb_paths draws of GP(0, k) at xt: C @ N(0, I) with K(xt, xt) = C C^T (core/sample_paths.py:18-63).
-        Only the Cholesky route exists on the device ('svd' is rejected, not emulated)."""
+        Only the Cholesky route exists on the device: method='svd' (the symmetric square root U sqrt(s) U^T,
+        :50-58, meant for covariance matrices Cholesky cannot factor) is refused loudly, not emulated.
+        check_result=True raises when K(xt, xt) is not positive definite (the reference's NaN check, :46-49);
+        False skips the device->host read of the status word and returns whatever the factorisation produced."""
         if method != "chol":
             if method == "svd":
                 raise _abi.GpmpError("sample_paths(method='svd') has no device implementation; use 'chol'")
@@ -260,15 +288,15 @@ class Model:
         xt_ = ops.to_device(xt)
         normals = torch.randn(xt_.shape[0], nb_paths, dtype=torch.float64, device=xt_.device,
                               generator=_generator())
-        return self.sample_paths_from_normals(xt_, normals)
+        return self.sample_paths_from_normals(xt_, normals, check_result=check_result)
 
-    def sample_paths_from_normals(self, xt, normals):
+    def sample_paths_from_normals(self, xt, normals, check_result=True):
         """Deterministic part of sample_paths: C @ normals (the map parity is defined on)."""
         xt_ = ops.to_device(xt)
         normals = ops.to_device(normals)
         with torch.no_grad():
             K = kernel.materialize(self.covariance(xt_, xt_, _as_param(self.covparam)))
-            fac = ops.potrf(K)  # raises LinAlgError when not PD (the reference checks for NaNs)
+            fac = ops.potrf(K, check_pd=bool(check_result))  # LinAlgError when not PD and checked
             nt = fac.n
             L = fac.A[:nt, :nt]
             Nt = ops.transpose(normals)  # paths x nt
@@ -319,7 +347,7 @@ class Fitted:
         self.ld = ops._round_ld(self.n)
         self.chunk = int(max(128, min(32768, (1 << 31) // (8 * self.ld))))
 
-    def _chunk(self, xtc, Pt, ktt, Vt, mode):
+    def _chunk(self, xtc, Pt, ktt, Vt, mode, return_dots=False):
         """One chunk through gpmp_predict_chunk; takes the callable's own cross-covariance when it is not the
         plain Matern of the same-set call."""
         model, state, n = self.model, self.state, self.n
@@ -330,16 +358,16 @@ class Fitted:
                     and getattr(state, "kernel", None) is not None and Kx.p == state.kernel[0]
                     and Kx.param is state.kernel[1])
             if same:
-                return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode)
+                return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode, return_dots)
             Vt[:, :n].copy_(kernel.materialize(Kx).t())
             saved, state.spec = state.spec, None
             try:
-                return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode)
+                return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode, return_dots)
             finally:
                 state.spec = saved
         Kx = kernel.materialize(model.covariance(self.xi, xtc, self.covparam))
         Vt[:, :n].copy_(Kx.t())
-        return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode)
+        return ops.predict_chunk(state, xtc, Pt, ktt, Vt, mode, return_dots)
 
     def _basis_and_prior(self, xt):
         model = self.model
@@ -376,6 +404,45 @@ class Fitted:
         if return_lambdas:
             return mean, var, lam_rows[:, :n].t()
         return mean, var
+
+    def weights_and_variance(self, xt, return_type=0):
+        """(lambda_t (n x m), posterior variance) like core/kriging.py's predictors: return_type -1 -> None,
+        0 -> marginal variances (m,), 1 -> posterior covariance matrix (m, m) = K_tt - V V^T + E E^T, where V rows are
+        the whitened cross-covariances and E rows the mean-basis corrections e_t (the reference
+        forms K_tt - [lambda; mu]^T [K_it; P_t^T], core/kriging.py:192-197).  Device tensors, variances not clamped."""
+        xt = ops.to_device(xt)
+        n, m, q = self.n, xt.shape[0], self.state.q
+        use_basis = q > 0
+        with torch.no_grad():
+            Pt = self.model._basis(xt).contiguous() if use_basis else None
+            ktt = ops.to_device(self.model.covariance(xt, None, self.covparam, pairwise=True)).reshape(-1).contiguous()
+            cov = None
+            if return_type == 1:
+                # pass 1: V (mode 0) and the e_t records of every chunk
+                V = ops._empty((m, self.ld))
+                E = ops._empty((m, ops._round_ld(max(q, 1)))) if use_basis else None
+                for c0 in range(0, m, self.chunk):
+                    c1 = min(m, c0 + self.chunk)
+                    _, _, dots = self._chunk(xt[c0:c1], None if Pt is None else Pt[c0:c1], ktt[c0:c1], V[c0:c1], 0,
+                                             return_dots=True)
+                    if use_basis:
+                        E[c0:c1, :q].copy_(dots[:, :q])
+                Ktt = kernel.materialize(self.model.covariance(xt, xt, self.covparam))
+                cov = ops.padded(Ktt)
+                ops.gemm_nt(V[:, :n], V[:, :n], C_out=cov, alpha=-1.0, beta=1.0)
+                if use_basis:
+                    ops.gemm_nt(E[:, :q], E[:, :q], C_out=cov, alpha=1.0, beta=1.0)
+                del V
+            lam_rows = ops._empty((m, self.ld))
+            var = ops._empty((m,))
+            for c0 in range(0, m, self.chunk):
+                c1 = min(m, c0 + self.chunk)
+                _, s2 = self._chunk(xt[c0:c1], None if Pt is None else Pt[c0:c1], ktt[c0:c1], lam_rows[c0:c1], 1)
+                var[c0:c1] = s2
+        lam = lam_rows[:, :n].t()
+        if return_type == -1:
+            return lam, None
+        return lam, (var if return_type == 0 else cov)
 
     def conditional_sample_paths_chunked(self, ztsim, xi_ind, xt, xt_ind, convert_out=True):
         """Conditioning by kriging without ever forming lambda_t (the reference's

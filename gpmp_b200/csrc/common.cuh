@@ -112,6 +112,43 @@ __device__ __forceinline__ double exp_neg(double t) {
     return t != t ? t : res;
 }
 
+// ---- short forms for the covariance tile kernels (K1 / K4): fewer FP64 operations and no conversion or
+// select chains (those kernels are bound by instruction issue, not by HBM) ------------------------------------
+// sqrt(a), a >= 0: one third-order step from the hardware seed y ~ a^-1/2 (relative error 2^-23):
+//   s = a y,  e = 1 - s y,  sqrt(a) = s (1 - e)^-1/2 = s (1 + e/2 + 3 e^2/8 + O(e^3)),  O(e^3) < 1e-20.
+// The seed is taken at a + 1e-300 so that a = 0 gives s = 0 and an exact 0 without a test; NaN propagates.
+__device__ __forceinline__ double sqrt_seeded(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a + 1e-300));
+    const double s = a * y;
+    const double e = fma(-s, y, 1.0);
+    const double t = fma(e, 0.375, 0.5) * e;
+    return fma(s, t, s);
+}
+
+// exp(-t) for 0 <= t <= 707 (the caller clamps), ~2 ulp:  K = round(32 t / ln 2) by the add-magic-number trick
+// (the integer lands in the low word of the sum: no FRND / F2I), r = K ln2/32 - t in [-ln2/64, ln2/64],
+// exp(-t) = 2^-(K>>5) * tab[K & 31] * exp(r) with tab[j] = 2^(-j/32) (32 doubles, passed in shared memory) and a
+// degree-6 Taylor polynomial (remainder 3.5e-18); the power of two goes straight into the exponent field.
+// A NaN argument gives an arbitrary finite result here: callers that can see NaN multiply by a NaN polynomial.
+constexpr int EXP_TAB = 32;
+__device__ __forceinline__ double exp_neg_tab(double t, const double* __restrict__ tab) {
+    const double d = fma(t, 46.16624130844683, 6755399441055744.0);  // 32 / ln 2 ; 1.5 * 2^52
+    const int K = __double2loint(d);
+    const double kf = d - 6755399441055744.0;
+    double r = fma(kf, 0.021660849392446835, -t);  // ln2/32, high 37 bits (K * hi is exact)
+    r = fma(kf, 5.145609244655338e-14, r);
+    double p = 1.3888888888888889e-03;
+    p = fma(p, r, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double e = tab[K & (EXP_TAB - 1)] * p;  // in (0.49, 1.02]
+    return __hiloint2double(__double2hiint(e) - ((K >> 5) << 20), __double2loint(e));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -168,5 +205,7 @@ inline GemmDesc gemm_desc() {
     return g;
 }
 int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream);
+// gemm_tma.cu: 0 launched, 1 not a shape / environment it serves (take the cp.async kernel), < 0 error
+int launch_gemm_nt_tma(const GemmDesc& g, cudaStream_t stream);
 
 }  // namespace gpmp

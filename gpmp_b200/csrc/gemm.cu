@@ -255,6 +255,11 @@ int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream) {
     // panel solves, A == C) must keep one column tile per row block, so N > 64 takes the 128-wide shape.
     const bool in_place = (g.A == g.C || g.B == g.C);
     if (in_place && g.N > 64) return launch_cfg<4, 4, 4, 4, 1>(g, stream);
+    // products that fill the machine with 128 x 128 tiles: the TMA / mbarrier kernel (gemm_tma.cu)
+    {
+        const int rc = launch_gemm_nt_tma(g, stream);
+        if (rc <= 0) return rc;
+    }
     // Latency shapes for launches that cannot fill the machine (the chain's K=128 updates in the tail of a
     // factorisation): a lone 64x64 tile costs 5 us + 0.8 us per 16-wide k step because one warp per scheduler
     // partition issues all its DMMAs; 32-row / 32x32 tiles spread the same work over 2x / 4x the SMs.

@@ -10,6 +10,8 @@ struct MaternDev {
     double dscale;               // -c^2/(2p-1) (p>=1) or -c (p==0): k'(h)/h = dscale*exp(-t)*q_{p-1}(t)
     double coef[GPMP_MAX_P];     // a_i, i=0..p-1:   q_p(t)     = 1 + sum a_i (2t)^(p-i)
     double coefm1[GPMP_MAX_P];   // a'_i, i=0..p-2:  q_{p-1}(t) = 1 + sum a'_i (2t)^(p-1-i)
+    double bq[GPMP_MAX_P + 1];   // the same polynomials in powers of t = c h (Horner by FMA): q_p(2t) = sum_k bq[k] t^k
+    double bqm1[GPMP_MAX_P + 1]; // q_{p-1}(2t) = sum_k bqm1[k] t^k  (k <= p-1)
     double invrho[GPMP_MAX_DIM];
 };
 

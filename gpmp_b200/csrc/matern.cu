@@ -28,6 +28,11 @@ int make_matern_dev(const gpmp_cov_spec* s, MaternDev* m, bool same_set) {
     for (int i = 0; i < GPMP_MAX_P; ++i) m->coef[i] = m->coefm1[i] = 0.0;
     matern_coef(s->p, m->coef);
     if (s->p >= 1) matern_coef(s->p - 1, m->coefm1);
+    // powers of t: (2t)^(p-i) = 2^(p-i) t^(p-i)
+    for (int k = 0; k <= GPMP_MAX_P; ++k) m->bq[k] = m->bqm1[k] = 0.0;
+    m->bq[0] = m->bqm1[0] = 1.0;
+    for (int i = 0; i < s->p; ++i) m->bq[s->p - i] = m->coef[i] * ldexp(1.0, s->p - i);
+    for (int i = 0; i + 1 < s->p; ++i) m->bqm1[s->p - 1 - i] = m->coefm1[i] * ldexp(1.0, s->p - 1 - i);
     for (int j = 0; j < GPMP_MAX_DIM; ++j) m->invrho[j] = j < s->d ? exp(s->loginvrho[j]) : 0.0;
     return GPMP_OK;
 }
@@ -84,66 +89,104 @@ __device__ __forceinline__ double matern_dk_over_h(const MaternDev& m, double h)
 }
 
 constexpr int CT = 64;          // tile edge
+constexpr int CTP = CT + 2;     // row stride of the staged point tiles [dim][point]: 2 doubles of padding spread the
+                                // dimension rows over the banks while the tile is filled (the fill walks the row-major
+                                // (point, dim) array, so consecutive threads write different dimension rows)
 constexpr int COV_THREADS = 256;
 
-// Kernel constants held in registers.  P >= 0: regularity known at compile time, Horner coefficients in
-// registers and fully unrolled (p = 0..4 cover every example of the reference but one); P == -1: any p up to
-// GPMP_MAX_P, coefficients read from the shared copy of MaternDev.
+// 2^(-j/32), j = 0..31, correctly rounded: the table of exp_neg_tab (staged into shared memory by the tile kernels)
+__device__ const double EXP2M_TAB[EXP_TAB] = {
+    1.0, 0.9785720620877001, 0.9576032806985737, 0.93708381705515,
+    0.9170040432046712, 0.8973545375015536, 0.8781260801866497, 0.859309649061239,
+    0.8408964152537145, 0.8228777390769825, 0.8052451659746271, 0.7879904225539432,
+    0.7711054127039704, 0.7545822137967114, 0.7384130729697497, 0.7225904034885233,
+    0.7071067811865476, 0.691954940981916, 0.6771277734684463, 0.6626183215798707,
+    0.6484197773255048, 0.6345254785958666, 0.620928906036742, 0.6076236799902345,
+    0.5946035575013605, 0.5818624293887887, 0.5693943173783458, 0.5571933712979462,
+    0.5452538663326288, 0.5335702003384118, 0.5221368912137069, 0.5109485743270583};
+
+constexpr double T_CLAMP = 707.0;  // exp(-707) = 8e-308: beyond it the kernel value is 0 (the reference underflows at 745)
+
+// Kernel constants held in registers.  P >= 0: regularity known at compile time, Horner coefficients (in powers
+// of t = c h, sigma2 folded in) in registers and fully unrolled (p = 0..4 cover every example of the reference but
+// one); P == -1: any p up to GPMP_MAX_P, coefficients read from the shared copy of MaternDev.
+// The tile kernels stage their points pre-scaled by c / rho_j, so the distance they accumulate IS t = c h.
 template <int P>
 struct MaternRegs {
-    static constexpr int NA = P > 0 ? P : 1, NB_ = P > 1 ? P - 1 : 1;
-    double c, sigma2, dscale;
-    double a[NA], am1[NB_];
+    static constexpr int NA = P > 0 ? P + 1 : 1, NB_ = P > 1 ? P : 1;
+    double sigma2, sdscale;    // sdscale = sigma2 * dscale
+    double bq[NA], bqm1[NB_];  // sigma2 q_p(2t) and sigma2 dscale q_{p-1}(2t) as polynomials in t
     const MaternDev* sm;
+    const double* tab;         // shared-memory copy of EXP2M_TAB
     int p;
-    __device__ __forceinline__ void init(const MaternDev* m) {
-        sm = m; p = m->p; c = m->c; sigma2 = m->sigma2; dscale = m->dscale;
+    __device__ __forceinline__ void init(const MaternDev* m, const double* exp_tab) {
+        sm = m; p = m->p; sigma2 = m->sigma2; sdscale = m->sigma2 * m->dscale; tab = exp_tab;
         if (P > 0) {
 #pragma unroll
-            for (int i = 0; i < NA; ++i) a[i] = m->coef[i];
+            for (int k = 0; k < NA; ++k) bq[k] = m->sigma2 * m->bq[k];
+        } else {
+            bq[0] = m->sigma2;
         }
         if (P > 1) {
 #pragma unroll
-            for (int i = 0; i < NB_; ++i) am1[i] = m->coefm1[i];
-        }
-    }
-    // q_p(2t)
-    __device__ __forceinline__ double poly(double u) const {
-        double acc = 0.0;
-        if (P >= 0) {
-#pragma unroll
-            for (int i = 0; i < P; ++i) acc = (acc + a[i]) * u;
+            for (int k = 0; k < NB_; ++k) bqm1[k] = sdscale * m->bqm1[k];
         } else {
-            for (int i = 0; i < p; ++i) acc = (acc + sm->coef[i]) * u;
+            bqm1[0] = sdscale;
         }
-        return 1.0 + acc;
     }
-    // q_{p-1}(2t)
-    __device__ __forceinline__ double polym1(double u) const {
-        double acc = 0.0;
+    // sigma2 q_p(2t)
+    __device__ __forceinline__ double poly(double t) const {
         if (P >= 0) {
+            double acc = bq[NA - 1];
 #pragma unroll
-            for (int i = 0; i < P - 1; ++i) acc = (acc + am1[i]) * u;
-        } else {
-            for (int i = 0; i < p - 1; ++i) acc = (acc + sm->coefm1[i]) * u;
+            for (int k = NA - 2; k >= 0; --k) acc = fma(acc, t, bq[k]);
+            return acc;
         }
-        return 1.0 + acc;
+        double acc = sm->bq[p];
+        for (int k = p - 1; k >= 0; --k) acc = fma(acc, t, sm->bq[k]);
+        return sigma2 * acc;
     }
-    // sigma2 * k_p(h) and, optionally, sigma2 * k_p'(h)/h (p >= 1) or sigma2 * k_0'(h) (p == 0)
-    __device__ __forceinline__ double cov(double h) const {
-        if (isinf(h)) h = GPMP_BIGF;
-        const double t = c * h;
-        return sigma2 * exp_neg(t) * poly(2.0 * t);
+    // sigma2 dscale q_{p-1}(2t)   (p >= 1)
+    __device__ __forceinline__ double polym1(double t) const {
+        if (P >= 0) {
+            double acc = bqm1[NB_ - 1];
+#pragma unroll
+            for (int k = NB_ - 2; k >= 0; --k) acc = fma(acc, t, bqm1[k]);
+            return acc;
+        }
+        double acc = sm->bqm1[p - 1];
+        for (int k = p - 2; k >= 0; --k) acc = fma(acc, t, sm->bqm1[k]);
+        return sdscale * acc;
     }
-    __device__ __forceinline__ void cov_and_dk(double h, double& kc, double& dkh) const {
-        if (isinf(h)) h = GPMP_BIGF;
-        const double t = c * h;
-        const double e = sigma2 * exp_neg(t);
-        kc = e * poly(2.0 * t);
+    // sigma2 k_p at t = c h (t >= 0, +inf or NaN).  t is clamped before the polynomial, so an infinite distance
+    // gives exactly 0 (the reference replaces inf by fmax/1000 first, torch_backend.py:500-502) and a NaN
+    // distance gives NaN through the polynomial (through a select for p = 0, which has none).
+    __device__ __forceinline__ double cov_t(double t) const {
+        const bool big = t > T_CLAMP;
+        const double tc = big ? T_CLAMP : t;
+        const double e = exp_neg_tab(tc, tab);
+        double k = e * poly(tc);
         const bool p0 = P >= 0 ? (P == 0) : (p == 0);
-        dkh = p0 ? dscale * e : dscale * e * polym1(2.0 * t);
+        if (p0) k = tc != tc ? tc : k;
+        return big ? 0.0 : k;
+    }
+    // sigma2 k_p(h) and sigma2 k_p'(h)/h (p >= 1) or sigma2 k_0'(h) (p == 0), at t = c h
+    __device__ __forceinline__ void cov_and_dk_t(double t, double& kc, double& dkh) const {
+        const bool big = t > T_CLAMP;
+        const double tc = big ? T_CLAMP : t;
+        const double e = exp_neg_tab(tc, tab);
+        const bool p0 = P >= 0 ? (P == 0) : (p == 0);
+        double k = e * poly(tc);
+        double dk = p0 ? sdscale * e : e * polym1(tc);
+        if (p0) { k = tc != tc ? tc : k; dk = tc != tc ? tc : dk; }
+        kc = big ? 0.0 : k;
+        dkh = big ? 0.0 : dk;
     }
 };
+
+__device__ __forceinline__ void stage_exp_tab(double* dst) {
+    if (threadIdx.x < EXP_TAB) dst[threadIdx.x] = EXP2M_TAB[threadIdx.x];
+}
 
 // Stage the parameter record in shared memory (from the per-batch device array or from the kernel
 // parameters) so that every later access is a shared-memory broadcast, not a generic load.
@@ -182,26 +225,32 @@ __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
     tj = t - (int)((long long)r * (r + 1) / 2);
 }
 
-__device__ __forceinline__ void stage_points(double (*s)[CT], const double* __restrict__ pts, int base, int npts,
-                                             const MaternDev& m, int tid) {
-    // s[j][r] = invrho[j] * pts[base + r][j]; coalesced over the row-major (point, dim) array
+__device__ __forceinline__ void stage_points(double* __restrict__ s, const double* __restrict__ pts, int base, int npts,
+                                             const MaternDev& m, int tid, double scale) {
+    // s[j][r] = scale * invrho[j] * pts[base + r][j]; coalesced over the row-major (point, dim) array.
+    // scale = c for covariance values (the accumulated distance is then t = c h), 1 for plain distances.
     const int d = m.d;
     for (int e = tid; e < CT * d; e += COV_THREADS) {
         int r = e / d, j = e - r * d;
         int gr = base + r;
-        s[j][r] = gr < npts ? m.invrho[j] * pts[(long long)gr * d + j] : 0.0;
+        s[j * CTP + r] = gr < npts ? (scale * m.invrho[j]) * pts[(long long)gr * d + j] : 0.0;
     }
 }
 
+// Shared memory (dynamic): x tile [d][CTP], y tile [d][CTP].  The parameter record is read straight from the kernel
+// parameters (constant bank) unless the launch is batched over per-entry records in device memory.
 template <int P>
-__global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a) {
-    __shared__ __align__(16) double xs[GPMP_MAX_DIM][CT];
-    __shared__ __align__(16) double ys[GPMP_MAX_DIM][CT];
+__global__ void __launch_bounds__(COV_THREADS, 4) matern_cov_kernel(const __grid_constant__ CovArgs a) {
+    extern __shared__ __align__(16) double cov_sm[];
     __shared__ MaternDev msh;
-    stage_matern(&msh, a.mdev ? a.mdev + blockIdx.z : nullptr, a.m);
-    const MaternDev& m = msh;
+    __shared__ double etab[EXP_TAB];
+    stage_exp_tab(etab);
+    if (a.mdev) stage_matern(&msh, a.mdev + blockIdx.z, a.m);
+    const MaternDev& m = a.mdev ? msh : a.m;
     MaternRegs<P> mr;
-    mr.init(&msh);
+    mr.init(&m, etab);
+    double* xs = cov_sm;
+    double* ys = cov_sm + (size_t)m.d * CTP;
     double* __restrict__ Kb = a.K + (long long)blockIdx.z * a.strideK;
     int ti, tj;
     if (a.mode == CM_RECT) {
@@ -212,8 +261,9 @@ __global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a
     }
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int r0 = ti * CT, c0 = tj * CT;
-    stage_points(xs, a.x + (long long)blockIdx.z * a.strideX, r0, a.n, m, tid);
-    stage_points(ys, a.y + (long long)blockIdx.z * a.strideX, c0, a.mcols, m, tid);
+    const double pscale = a.dist_only ? 1.0 : m.c;
+    stage_points(xs, a.x + (long long)blockIdx.z * a.strideX, r0, a.n, m, tid, pscale);
+    stage_points(ys, a.y + (long long)blockIdx.z * a.strideX, c0, a.mcols, m, tid, pscale);
     __syncthreads();
 
     double h2[4][4];
@@ -222,10 +272,10 @@ __global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a
 #pragma unroll
         for (int j = 0; j < 4; ++j) h2[i][j] = 0.0;
     for (int j = 0; j < m.d; ++j) {
-        const double2 xa = *reinterpret_cast<const double2*>(&xs[j][ty * 4]);
-        const double2 xb = *reinterpret_cast<const double2*>(&xs[j][ty * 4 + 2]);
-        const double2 ya = *reinterpret_cast<const double2*>(&ys[j][2 * tx]);
-        const double2 yb = *reinterpret_cast<const double2*>(&ys[j][32 + 2 * tx]);
+        const double2 xa = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4]);
+        const double2 xb = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4 + 2]);
+        const double2 ya = *reinterpret_cast<const double2*>(&ys[j * CTP + 2 * tx]);
+        const double2 yb = *reinterpret_cast<const double2*>(&ys[j * CTP + 32 + 2 * tx]);
         const double xr[4] = {xa.x, xa.y, xb.x, xb.y};
         const double yc[4] = {ya.x, ya.y, yb.x, yb.y};
 #pragma unroll
@@ -241,8 +291,8 @@ __global__ void __launch_bounds__(COV_THREADS) matern_cov_kernel(const CovArgs a
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double h = fast_sqrt(h2[i][k]);
-            v[i][k] = a.dist_only ? h : mr.cov(h);
+            const double t = sqrt_seeded(h2[i][k]);  // c h (covariance) or h (distance)
+            v[i][k] = a.dist_only ? t : mr.cov_t(t);
         }
     const bool sym = a.mode != CM_RECT;
     const double diag_add = m.diag_add;
@@ -333,13 +383,14 @@ int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batc
     bytes += 8.0 * (double)(n + (same ? 0 : a.mcols)) * spec->d;
     LaunchScope scope(KC_MATERN, bytes * batch, stream);
     dim3 grid((unsigned)ntiles, 1, (unsigned)batch);
+    const size_t cov_smem = (size_t)2 * spec->d * CTP * sizeof(double);  // x and y tiles: <= 33 KB at d = 32
     switch (dist_only ? 0 : spec->p) {
-        case 0: matern_cov_kernel<0><<<grid, COV_THREADS, 0, stream>>>(a); break;
-        case 1: matern_cov_kernel<1><<<grid, COV_THREADS, 0, stream>>>(a); break;
-        case 2: matern_cov_kernel<2><<<grid, COV_THREADS, 0, stream>>>(a); break;
-        case 3: matern_cov_kernel<3><<<grid, COV_THREADS, 0, stream>>>(a); break;
-        case 4: matern_cov_kernel<4><<<grid, COV_THREADS, 0, stream>>>(a); break;
-        default: matern_cov_kernel<-1><<<grid, COV_THREADS, 0, stream>>>(a); break;
+        case 0: matern_cov_kernel<0><<<grid, COV_THREADS, cov_smem, stream>>>(a); break;
+        case 1: matern_cov_kernel<1><<<grid, COV_THREADS, cov_smem, stream>>>(a); break;
+        case 2: matern_cov_kernel<2><<<grid, COV_THREADS, cov_smem, stream>>>(a); break;
+        case 3: matern_cov_kernel<3><<<grid, COV_THREADS, cov_smem, stream>>>(a); break;
+        case 4: matern_cov_kernel<4><<<grid, COV_THREADS, cov_smem, stream>>>(a); break;
+        default: matern_cov_kernel<-1><<<grid, COV_THREADS, cov_smem, stream>>>(a); break;
     }
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
@@ -407,16 +458,24 @@ struct ContractArgs {
     const MaternDev* mdev; long long strideG, strideU, strideX;
 };
 
+// Shared memory (dynamic): x tile [d][CT], y tile [d][CT], U rows at the tile's rows [r][CT] and at its columns
+// [r][CT] -- every entry of the tile reads its 2 r correction values from there, not from global memory.
 template <int P>
-__global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArgs a) {
-    __shared__ __align__(16) double xs[GPMP_MAX_DIM][CT];
-    __shared__ __align__(16) double ys[GPMP_MAX_DIM][CT];
+__global__ void __launch_bounds__(COV_THREADS, 2) contract_kernel(const __grid_constant__ ContractArgs a) {
+    extern __shared__ __align__(16) double csm[];
     __shared__ double wacc[COV_THREADS / 32][GPMP_MAX_DIM + 2];
     __shared__ MaternDev msh;
-    stage_matern(&msh, a.mdev ? a.mdev + blockIdx.z : nullptr, a.m);
-    const MaternDev& m = msh;
+    __shared__ double etab[EXP_TAB];
+    stage_exp_tab(etab);
+    if (a.mdev) stage_matern(&msh, a.mdev + blockIdx.z, a.m);
+    const MaternDev& m = a.mdev ? msh : a.m;
     MaternRegs<P> mr;
-    mr.init(&msh);
+    mr.init(&m, etab);
+    const int d = m.d, nr = a.Ut ? a.r : 0;
+    double* xs = csm;
+    double* ys = csm + (size_t)d * CTP;
+    double (*ur)[CT] = reinterpret_cast<double (*)[CT]>(csm + (size_t)2 * d * CTP);
+    double (*uc)[CT] = reinterpret_cast<double (*)[CT]>(csm + (size_t)2 * d * CTP + (size_t)nr * CT);
     const long long zb = blockIdx.z;
     const double* __restrict__ Gz = a.G + zb * a.strideG;
     const double* __restrict__ Uz = a.Ut ? a.Ut + zb * a.strideU : nullptr;
@@ -425,8 +484,17 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
     else { ti = blockIdx.x / a.tiles_n; tj = blockIdx.x - ti * a.tiles_n; }
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
     const int r0 = ti * CT, c0 = tj * CT;
-    stage_points(xs, a.x + zb * a.strideX, r0, a.n, m, tid);
-    stage_points(ys, a.y + zb * a.strideX, c0, a.mcols, m, tid);
+    // points pre-scaled by c / rho_j (plain 1 / rho_j for the distance vjp): the accumulated distance is t = c h,
+    // and the squared differences of the second pass carry c^2, which is folded into the weights
+    const double pscale = a.dist_only ? 1.0 : m.c;
+    const double inv_c = 1.0 / pscale, inv_c2 = inv_c * inv_c;
+    stage_points(xs, a.x + zb * a.strideX, r0, a.n, m, tid, pscale);
+    stage_points(ys, a.y + zb * a.strideX, c0, a.mcols, m, tid, pscale);
+    for (int e = tid; e < nr * CT; e += COV_THREADS) {
+        const int q = e / CT, i = e - q * CT;
+        ur[q][i] = r0 + i < a.n ? Uz[(long long)q * a.ldu + r0 + i] : 0.0;
+        uc[q][i] = c0 + i < a.mcols ? Uz[(long long)q * a.ldu + c0 + i] : 0.0;
+    }
     __syncthreads();
 
     double h2[4][4];
@@ -434,11 +502,11 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int k = 0; k < 4; ++k) h2[i][k] = 0.0;
-    for (int j = 0; j < m.d; ++j) {
-        const double2 xa = *reinterpret_cast<const double2*>(&xs[j][ty * 4]);
-        const double2 xb = *reinterpret_cast<const double2*>(&xs[j][ty * 4 + 2]);
-        const double2 ya = *reinterpret_cast<const double2*>(&ys[j][2 * tx]);
-        const double2 yb = *reinterpret_cast<const double2*>(&ys[j][32 + 2 * tx]);
+    for (int j = 0; j < d; ++j) {
+        const double2 xa = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4]);
+        const double2 xb = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4 + 2]);
+        const double2 ya = *reinterpret_cast<const double2*>(&ys[j * CTP + 2 * tx]);
+        const double2 yb = *reinterpret_cast<const double2*>(&ys[j * CTP + 32 + 2 * tx]);
         const double xr[4] = {xa.x, xa.y, xb.x, xb.y};
         const double yc[4] = {ya.x, ya.y, yb.x, yb.y};
 #pragma unroll
@@ -449,38 +517,77 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
                 h2[i][k] = fma(df, df, h2[i][k]);
             }
     }
-    // weights w = G_ik * sigma2 * k'(h)/h (x2 for strictly-lower entries in sym mode)
+    // G tile entries of this thread: rows r0 + 4 ty + i, columns c0 + {2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx}
+    const bool diag_tile = a.sym && ti == tj;
+    // interior: no bounds, no triangle mask, no trace entries (a same-set tile on the diagonal has them even in the
+    // rectangular form), 16-byte loads
+    const bool interior = !(ti == tj && (a.sym || a.same_set)) && r0 + CT <= a.n && c0 + CT <= a.mcols &&
+                          (a.ldg & 1) == 0 && (reinterpret_cast<uintptr_t>(Gz) & 15) == 0;
+    double gv[4][4];
+    if (interior) {
+        const double* gp = Gz + (long long)(r0 + ty * 4) * a.ldg + c0 + 2 * tx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 g0 = *reinterpret_cast<const double2*>(gp);
+            const double2 g1 = *reinterpret_cast<const double2*>(gp + 32);
+            gv[i][0] = g0.x; gv[i][1] = g0.y; gv[i][2] = g1.x; gv[i][3] = g1.y;
+            gp += a.ldg;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = r0 + ty * 4 + i;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = c0 + 32 * (k >> 1) + 2 * tx + (k & 1);
+                const bool live = row < a.n && col < a.mcols && !(diag_tile && col > row);
+                gv[i][k] = live ? Gz[(long long)row * a.ldg + col] : 0.0;
+            }
+        }
+    }
+    // low-rank correction G - U^T U from the staged rows (dead entries keep 0 through the weight below)
+    for (int q = 0; q < nr; ++q) {
+        const double2 ua = *reinterpret_cast<const double2*>(&ur[q][ty * 4]);
+        const double2 ub = *reinterpret_cast<const double2*>(&ur[q][ty * 4 + 2]);
+        const double2 va = *reinterpret_cast<const double2*>(&uc[q][2 * tx]);
+        const double2 vb = *reinterpret_cast<const double2*>(&uc[q][32 + 2 * tx]);
+        const double uu[4] = {ua.x, ua.y, ub.x, ub.y};
+        const double vv[4] = {va.x, va.y, vb.x, vb.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gv[i][k] = fma(-uu[i], vv[k], gv[i][k]);
+    }
+    // weights w = G_ik * sigma2 * k'(h)/h / c^2 (x2 for strictly-lower entries in sym mode)
     double w[4][4];
     double sK = 0.0, sTr = 0.0;
-    const bool diag_tile = a.sym && ti == tj;
+    const double off_mult = a.sym ? 2.0 : 1.0;  // off-diagonal tiles of the symmetric form count twice
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = r0 + ty * 4 + i;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int col = c0 + 32 * (k >> 1) + 2 * tx + (k & 1);
-            double gv = 0.0, mult = 1.0;
-            bool live = row < a.n && col < a.mcols;
-            if (a.sym) {
-                if (diag_tile && col > row) live = false;
-                if (col < row) mult = 2.0;
+            double mult = off_mult, g = gv[i][k];
+            if (!interior) {
+                const bool live = row < a.n && col < a.mcols && !(diag_tile && col > row);
+                if (a.sym && col >= row) mult = 1.0;
+                if (!live) { g = 0.0; mult = 0.0; }
+                if (a.same_set && live && row == col) sTr += g;
             }
-            if (live) {
-                gv = Gz[(long long)row * a.ldg + col];
-                for (int q = 0; q < a.r; ++q) gv -= Uz[(long long)q * a.ldu + row] * Uz[(long long)q * a.ldu + col];
-            }
-            const double h = fast_sqrt(h2[i][k]);
+            const double t = sqrt_seeded(h2[i][k]);
             double dkh, kc;
             if (a.dist_only) {
-                dkh = h > 0.0 ? 1.0 / h : 0.0;  // reference: custom_sqrt has zero gradient at 0
+                dkh = t > 0.0 ? 1.0 / t : 0.0;  // reference: custom_sqrt has zero gradient at 0
                 kc = 0.0;
             } else {
-                mr.cov_and_dk(h, kc, dkh);  // both already carry sigma2
-                if (m.p == 0) dkh = h > 0.0 ? dkh / h : 0.0;  // reference: masked sqrt gradient at 0
+                mr.cov_and_dk_t(t, kc, dkh);  // both already carry sigma2
+                const bool p0 = P >= 0 ? (P == 0) : (m.p == 0);
+                if (p0) dkh = t > 0.0 ? dkh / (t * inv_c) : 0.0;  // reference: masked sqrt gradient at 0
             }
-            sK += mult * gv * kc;
-            if (a.same_set && live && row == col) sTr += gv;
-            w[i][k] = live ? mult * gv * dkh : 0.0;
+            const double mg = mult * g;
+            sK = fma(mg, kc, sK);
+            w[i][k] = mg * (dkh * inv_c2);
         }
     }
     // per-dimension sums: warp-reduce each, lane 0 keeps the warp's running value in smem
@@ -488,30 +595,31 @@ __global__ void __launch_bounds__(COV_THREADS) contract_kernel(const ContractArg
         double t0 = warp_sum(sK), t1 = warp_sum(sTr);
         if (lane == 0) { wacc[warp][0] = t0; wacc[warp][1] = t1; }
     }
-    for (int j = 0; j < m.d; ++j) {
-        const double2 xa = *reinterpret_cast<const double2*>(&xs[j][ty * 4]);
-        const double2 xb = *reinterpret_cast<const double2*>(&xs[j][ty * 4 + 2]);
-        const double2 ya = *reinterpret_cast<const double2*>(&ys[j][2 * tx]);
-        const double2 yb = *reinterpret_cast<const double2*>(&ys[j][32 + 2 * tx]);
+    for (int j = 0; j < d; ++j) {
+        const double2 xa = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4]);
+        const double2 xb = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4 + 2]);
+        const double2 ya = *reinterpret_cast<const double2*>(&ys[j * CTP + 2 * tx]);
+        const double2 yb = *reinterpret_cast<const double2*>(&ys[j * CTP + 32 + 2 * tx]);
         const double xr[4] = {xa.x, xa.y, xb.x, xb.y};
         const double yc[4] = {ya.x, ya.y, yb.x, yb.y};
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double df = xr[i] - yc[k];
-                s = fma(w[i][k], df * df, s);
+            for (int k = 0; k < 4; k += 2) {
+                const double d0 = xr[i] - yc[k], d1 = xr[i] - yc[k + 1];
+                s0 = fma(w[i][k], d0 * d0, s0);
+                s1 = fma(w[i][k + 1], d1 * d1, s1);
             }
-        s = warp_sum(s);
+        const double s = warp_sum(s0 + s1);
         if (lane == 0) wacc[warp][2 + j] = s;
     }
     __syncthreads();
-    if (tid < 2 + m.d) {
+    if (tid < 2 + d) {
         double t = 0.0;
 #pragma unroll
         for (int wv = 0; wv < COV_THREADS / 32; ++wv) t += wacc[wv][tid];
-        a.partial[((long long)blockIdx.z * gridDim.x + blockIdx.x) * (2 + m.d) + tid] = t;
+        a.partial[((long long)blockIdx.z * gridDim.x + blockIdx.x) * (2 + d) + tid] = t;
     }
 }
 
@@ -587,13 +695,27 @@ int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const dou
     {
         double bytes = sym ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
         LaunchScope scope(KC_CONTRACT, bytes, stream);
-        if (nblocks > 0) switch (dist_only ? 0 : spec->p) {
-            case 0: contract_kernel<0><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
-            case 1: contract_kernel<1><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
-            case 2: contract_kernel<2><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
-            case 3: contract_kernel<3><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
-            case 4: contract_kernel<4><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
-            default: contract_kernel<-1><<<cgrid, COV_THREADS, 0, stream>>>(a); break;
+        // x / y tiles and the U rows of the tile: 2 (d + r) rows of CT doubles (<= 2 (32 + 32) 64 8 = 64 KB > 48 KB
+        // only when both d and r are near their limits: those launches opt in to the larger carve-out)
+        const size_t smem = ((size_t)2 * spec->d * CTP + (size_t)2 * (Ut ? r : 0) * CT) * sizeof(double);
+        auto launch = [&](auto kern) -> int {
+            if (smem > 48 * 1024 &&
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return GPMP_ERR_CUDA;
+            kern<<<cgrid, COV_THREADS, smem, stream>>>(a);
+            return GPMP_OK;
+        };
+        if (nblocks > 0) {
+            int lrc;
+            switch (dist_only ? 0 : spec->p) {
+                case 0: lrc = launch(contract_kernel<0>); break;
+                case 1: lrc = launch(contract_kernel<1>); break;
+                case 2: lrc = launch(contract_kernel<2>); break;
+                case 3: lrc = launch(contract_kernel<3>); break;
+                case 4: lrc = launch(contract_kernel<4>); break;
+                default: lrc = launch(contract_kernel<-1>); break;
+            }
+            if (lrc) return lrc;
         }
         GPMP_CHECK_LAUNCH();
     }

@@ -1320,7 +1320,11 @@ static int trailing_update(const PotrfCtx& c, int k, const double* Pnl, long lon
 // Library-owned streams and events of the look-ahead pipeline: one set per (device, caller stream), so two
 // caller streams that factor concurrently never share chain streams or reuse each other's events (the ABI is
 // re-entrant per (stream, workspace)).  The sets live for the life of the process.
-constexpr int LA_DEPTH = 4;  // look-ahead depth: the chain may run this many column groups ahead of the bulk
+constexpr int LA_DEPTH = 4;    // deepest look-ahead the stream / event sets are sized for
+constexpr int LA_DEFAULT = 1;  // depth used: measured at n = 8192 (value, ms): depth 1 8.96, 2 9.10, 4 9.17 -- under a
+                               // running bulk update the chain's whole-SM kernels (tile kernel 133 KB, panel solve
+                               // 229 KB of shared memory) wait for SMs to drain, so the chain is slower than the bulk
+                               // even while the trailing matrix is large and a deeper window has no lead to bank
 struct LookAhead {
     cudaStream_t caller = nullptr;
     int dev = -1;
@@ -1369,14 +1373,12 @@ static LookAhead* lookahead(cudaStream_t caller, int nevents) {
 //   Tlo/Tup compact diagonal-block inverses: nblk blocks of NB x NB (ld NB), block b at b*NB*NB
 //   W      panel scratch: TWO buffers of max(nrows, NB) x NB (ld NB) per batch entry, the second at
 //          W + Wrows*NB (the in-group updates of one group read its buffer while the next group fills the other)
-// Single matrices with several column groups run a depth-D look-ahead (D = LA_DEPTH): the caller's stream does
-// the bulk of every K=NB trailing update -- the column groups more than D ahead -- while library-owned priority
-// streams bring the next D groups up to date one (panel, group) product at a time and run the 128-wide steps of
-// the next group.  The latency-bound chain therefore runs up to D groups ahead of the bulk while the trailing
-// matrix is large, and that lead pays for the tail of the factorisation, where a group's bulk update is shorter
-// than its chain (n = 8192: sum of the chain steps 4.8 ms, sum of the updates 5.9 ms; with depth 1 the two
-// alternate instead of overlapping).  Trailing updates read the solved panel straight from A (its final place;
-// nothing writes it again), so the lagging bulk never holds a panel buffer.
+// Single matrices with several column groups run a depth-D look-ahead (D = LA_DEFAULT, up to LA_DEPTH): the
+// caller's stream does the bulk of every K=NB trailing update -- the column groups more than D ahead -- while
+// library-owned priority streams bring the next D groups up to date one (panel, group) product at a time and run
+// the 128-wide steps of the next group, so the chain may run up to D groups ahead of the bulk.  Trailing updates
+// read the solved panel straight from A (its final place; nothing writes it again), so a lagging bulk never holds
+// a panel buffer.
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
                cudaStream_t stream, double* Tsub, long long strideTsub, int tsub_tiles) {
@@ -1413,7 +1415,7 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
     // (stream order is the read-modify-write order of the group's columns).  Events order every other
     // read-modify-write of a column block.
     static const int forced_depth = dev_env("GPMP_DEV_LA");
-    const int D = min(forced_depth > 0 ? min(forced_depth, LA_DEPTH) : LA_DEPTH, nblk - 1);
+    const int D = min(forced_depth > 0 ? min(forced_depth, LA_DEPTH) : LA_DEFAULT, nblk - 1);
     // profiling mode 2 (gpmp_prof_enable(2)): the same launches, all on the caller's stream, so the per-class
     // CUDA-event times are exclusive kernel times
     const bool serial = prof().enabled == 2;

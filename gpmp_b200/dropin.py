@@ -17,8 +17,9 @@ CPU `gnp` namespace they are written against stay GPmp's):
   model seam    gpmp.core.Model methods on the path (gpmp/core/model.py:227-683): the three likelihoods, predict,
                 loo, norm_k_sqrd*, k_inverses, fisher_information*, sample_paths, conditional_sample_paths*
                                                                              -> gpmp_b200.core.Model
-  sampler seam  the per-particle loop of `logpdf_temp` (mcmc/param_posterior.py:752) when the selection criterion
-                is a `BatchableCriterion`                                    -> gpmp_b200.batched.BatchedCriterion
+  sampler seam  the per-particle loop of `logpdf_temp` (mcmc/param_posterior.py:752) and the per-chain loop of
+                MetropolisHastings.run_samples (mcmc/mh.py:412-443) when the selection criterion is a
+                `BatchableCriterion`                                         -> gpmp_b200.batched.BatchedCriterion
 
 Conventions that make the seams fit: covariance parameters, priors and the optimiser's vectors stay HOST tensors
 (SciPy needs them there); array data (xi, zi, xt) is moved to the current CUDA device at the Model boundary; the
@@ -129,10 +130,8 @@ def _wrap_run_smc(original):
 def _criterion_behind(fn):
     """The BatchableCriterion (and box) closed over by param_posterior's `logpdf_temp`, if that is what fn is."""
     try:
-        cells = dict(zip(fn.__code__.co_freevars, (c.cell_contents for c in fn.__closure__ or ())))
-        scalar = cells.get("_criterion_scalar")
-        inner = dict(zip(scalar.__code__.co_freevars, (c.cell_contents for c in scalar.__closure__ or ())))
-        f = inner.get("f")
+        cells = _closure_cells(fn)
+        f = _closure_cells(cells.get("_criterion_scalar")).get("f")
     except AttributeError:
         return None, None, None
     if isinstance(f, BatchableCriterion):
@@ -140,6 +139,69 @@ def _criterion_behind(fn):
         to_np = lambda b: None if b is None else np.asarray(b.detach().cpu() if hasattr(b, "detach") else b)
         return f, to_np(lo), to_np(hi)
     return None, None, None
+
+
+def _closure_cells(fn):
+    return dict(zip(fn.__code__.co_freevars, (c.cell_contents for c in fn.__closure__ or ())))
+
+
+def _mh_target_behind(log_target):
+    """(criterion, lower, upper, temperature) closed over by param_posterior._make_log_prob_mh's `log_prob`
+    (mcmc/param_posterior.py:229-252) when the criterion is a BatchableCriterion, else None."""
+    try:
+        cells = _closure_cells(log_target)
+    except AttributeError:
+        return None
+    f = cells.get("selection_criterion")
+    if not isinstance(f, BatchableCriterion):
+        return None
+    to_np = lambda b: None if b is None else np.asarray(b.detach().cpu() if hasattr(b, "detach") else b)
+    return f, to_np(cells.get("lower_b")), to_np(cells.get("upper_b")), float(cells.get("temperature", 1.0))
+
+
+def _wrap_mh_run_samples(original):
+    """MetropolisHastings.run_samples (mcmc/mh.py:412-443) walks the chains one by one, one `log_target` call per
+    chain and step.  The chains of one step are independent, so with a BatchableCriterion behind `log_target` all
+    proposals of a step are evaluated in ONE batched sweep.  Proposals and acceptance uniforms are drawn chain by
+    chain in the reference's order, so the random stream -- and therefore the trajectory -- is the reference's."""
+    import math
+
+    @functools.wraps(original)
+    def run_samples(self, n_steps, show_global_progress=False):
+        spec = _mh_target_behind(self.log_target)
+        if spec is None or not self.symmetric:
+            return original(self, n_steps, show_global_progress)
+        import gpmp.num as gnp
+
+        crit, lower, upper, temperature = spec
+        logpdf = _batched_logpdf(crit, lower, upper)
+        C = self.n_chains
+        i0 = self.global_iter + 1
+        i1 = i0 + n_steps
+        for t in range(i0, i1):
+            prev = [self.log_target_values[c, t - 1] for c in range(C)]
+            stale = [c for c in range(C) if prev[c] is None or bool(gnp.isnan(gnp.asarray(prev[c])))]
+            if stale:  # first step of a run: the current states have no stored log-target yet
+                vals = logpdf(gnp.to_np(gnp.stack([self.x[c, t - 1] for c in stale])), temperature)
+                for c, v in zip(stale, vals):
+                    prev[c] = float(v)
+            ys, us = [], []
+            for c in range(C):
+                ys.append(self.prop_rnd(self.x[c, t - 1], c))
+                us.append(max(gnp.to_scalar(gnp.rand()), 1e-300))
+            new = logpdf(gnp.to_np(gnp.stack(ys)), temperature)
+            for c in range(C):
+                lp_x, lp_y = float(prev[c]), float(new[c])
+                if math.log(us[c]) < lp_y - lp_x:
+                    self.x[c, t], self.accept[c, t], self.log_target_values[c, t] = ys[c], True, lp_y
+                else:
+                    self.x[c, t], self.accept[c, t], self.log_target_values[c, t] = self.x[c, t - 1], False, lp_x
+            self.global_iter += 1
+            if show_global_progress and self.global_iter % self.options.progress_interval == 0:
+                self._print_progress(self.global_iter, self.global_total, self.start_time)
+        return gnp.mean(self.accept[:, i0:i1], axis=1)
+
+    return run_samples
 
 
 def install(gp=None):
@@ -173,6 +235,8 @@ def install(gp=None):
         if hasattr(model_mod.Model, name):
             patch(model_mod.Model, name, _delegate(name))
     patch(post, "run_smc_sampling", _wrap_run_smc(post.run_smc_sampling))
+    mh = importlib.import_module("gpmp.mcmc.mh")
+    patch(mh.MetropolisHastings, "run_samples", _wrap_mh_run_samples(mh.MetropolisHastings.run_samples))
 
 
 def uninstall():

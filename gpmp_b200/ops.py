@@ -626,10 +626,12 @@ def likelihood_from_K(K, z, P):
 # --------------------------------------------------------------------------------------------------
 # L2: prediction
 # --------------------------------------------------------------------------------------------------
-def predict_chunk(state, xt, Pt, ktt, Vt, want_lambda):
+def predict_chunk(state, xt, Pt, ktt, Vt, want_lambda, return_dots=False):
     """One chunk of test points against a fitted state; returns (mean, var) device vectors; Vt is
-    overwritten: want_lambda = 0 scratch, 1 rows lambda_t^T, 2 rows w_t = v_t - Q~ e_t (the kriging weights
-    in whitened coordinates: lambda_t = L^-T w_t)."""
+    overwritten: want_lambda = 0 rows v_t = L^-1 k(xi, x_t) (the whitened cross-covariances), 1 rows lambda_t^T,
+    2 rows w_t = v_t - Q~ e_t (the kriging weights in whitened coordinates: lambda_t = L^-T w_t).
+    return_dots: also return the per-point record the row pass leaves in the scratch, (m, q + 2):
+    e_t = Q~^T v_t - R~^-T p_t (q entries), v_t . r, |v_t|^2  (posterior covariances need e_t)."""
     m = Vt.shape[0]
     n, q = state.n, state.q
     sbytes = lib().gpmp_predict_scratch_bytes(n, q, m)
@@ -640,6 +642,11 @@ def predict_chunk(state, xt, Pt, ktt, Vt, want_lambda):
                                    state.work.numel(), ptr(xt), m, ptr(Pt), ptr(ktt), ptr(Vt), _ld(Vt),
                                    ptr(scratch), scratch.numel(), ptr(mean), ptr(var), int(want_lambda),
                                    stream_ptr()), "gpmp_predict_chunk")
+    if return_dots:
+        NB = lib().gpmp_lik_dist_block(n)
+        off = (m * NB * 8 + 255) // 256 * 256
+        dots = scratch[off: off + m * (q + 2) * 8].view(torch.float64).view(m, q + 2)
+        return mean, var, dots
     return mean, var
 
 

@@ -228,9 +228,14 @@ int gpmp_lik_loo(int n, int q, void* work_dev, size_t work_bytes, const double* 
  *     has put a user-composed K(xt, xi) there.  On exit: rows lambda_t^T if want_lambda, else scratch.
  *   Pt_dev (m x q) mean basis at xt (NULL when q == 0);  ktt_dev[m] prior variances (NULL: sigma2).
  *   mean_dev[m], var_dev[m] outputs (variance not clamped: Model.predict clamps and warns).
- *   want_lambda: 0 Vt is scratch on exit; 1 rows lambda_t^T; 2 rows w_t = v_t - Q~ e_t, the kriging weights in
- *   whitened coordinates (lambda_t = L^-T w_t): conditioning of sample paths needs only W (L^-1 delta)^T, so
- *   the n x m weight matrix of gpmp/core/sample_paths.py:66-182 is never formed. */
+ *   want_lambda: 0 Vt holds the whitened cross-covariances v_t = L^-1 k(xi, x_t) on exit; 1 rows lambda_t^T;
+ *   2 rows w_t = v_t - Q~ e_t, the kriging weights in whitened coordinates (lambda_t = L^-T w_t): conditioning
+ *   of sample paths needs only W (L^-1 delta)^T, so the n x m weight matrix of
+ *   gpmp/core/sample_paths.py:66-182 is never formed.
+ *   scratch_dev: m x NB doubles of solve scratch (NB = gpmp_lik_dist_block(n)), then, 256-byte aligned, the
+ *   per-point record (m x (q + 2)): e_t = Q~^T v_t - R~^-T p_t (q entries), v_t . r, |v_t|^2.  The full posterior
+ *   covariance (return_type = 1 of gpmp/core/kriging.py:170-199) is K_tt - V V^T + E E^T from Vt (mode 0) and
+ *   the e_t of that record. */
 size_t gpmp_predict_scratch_bytes(int n, int q, int m);
 int gpmp_predict_chunk(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, void* work_dev,
                        size_t work_bytes, const double* xt_dev, int m, const double* Pt_dev,

@@ -127,3 +127,27 @@ def test_reference_smc_runs_on_batched_sweeps(bound):
     for i in range(5):
         v = float(model.negative_log_restricted_likelihood(gnp.asarray(th[i]), gnp.asarray(x), gnp.asarray(z)))
         assert abs(vals[i] - v) <= 1e-9 * max(1.0, abs(v))
+
+
+def test_reference_mh_runs_on_batched_steps(bound):
+    """Adaptive Metropolis-Hastings by the reference's sampler (mcmc/mh.py, 4 chains): one batched sweep per step
+    instead of one criterion call per chain.  Proposals and uniforms are drawn in the reference's order from the
+    same seeded generators, so the whole trajectory must reproduce the reference's CPU run."""
+    gp, gnp, b200 = bound
+    z_ = np.load(os.path.join(GOLDEN_DIR, "reference_extra.npz"))
+    g = {k.split("/", 1)[1]: z_[k] for k in z_.files if k.startswith("mh_small/")}
+    x, z, box = cases.smc_small()
+    crit = b200.BatchableCriterion(_model(gp, gnp, 2), x, z, 2, kind="reml")
+    gnp.set_seed(5)
+    torch.manual_seed(5)
+    samples, mh = gp.mcmc.sample_from_selection_criterion_mh(
+        selection_criterion=crit, param_initial_states=g["starts"], n_chains=4, n_steps_total=160, burnin_period=60,
+        sampling_box=box, silent=True, plot_chains=False, plot_empirical_distributions=False)
+    S = gnp.to_np(samples)
+    same_accepts = float(np.mean(gnp.to_np(mh.accept) == g["accept"]))
+    err = float(np.max(np.abs(S - g["samples"])))
+    print(f"[parity] MH 4 chains x 160 steps: {crit.sweeps} sweeps for {crit.evaluations} evaluations; identical "
+          f"accept/reject decisions {same_accepts:.3f}; max |sample - reference| {err:.2e}")
+    assert S.shape == g["samples"].shape
+    assert crit.sweeps <= 161 + 1 and crit.evaluations >= 4 * 160
+    assert same_accepts == 1.0 and err <= 1e-8
