@@ -13,6 +13,7 @@
 //   one iteration after the stage was consumed, when its release has normally already happened.
 //   Out-of-range rows / k are zero-filled by the TMA unit, so ragged M, N, K need no predicates on the load side.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gpmp {
@@ -253,6 +254,11 @@ int launch_gemm_nt_tma(const GemmDesc& g, cudaStream_t stream) {
     if (g.batch != 1 || g.batch2 != 1) return 1;
     if (g.A == g.C || g.B == g.C) return 1;  // in-place products keep the single-column-tile kernel
     if (g.K < TBK || (g.lda & 1) || (g.ldb & 1)) return 1;
+    // Short k loops stay on the 64 x 64 kernel: with one 128 x 128 CTA per SM nothing covers a tile's prologue and
+    // epilogue, and at K = 512 they are ~15 % of its life (measured, n = 8192 SYRK, TFLOP/s: K = 128 19.5 vs 24.0,
+    // K = 256 24.5 vs 29.3, K = 512 28.3 vs 30.9; K = 8192 35.4 vs 32.8).  Development knob: GPMP_DEV_TMA_MINK.
+    static const int min_k = getenv("GPMP_DEV_TMA_MINK") ? atoi(getenv("GPMP_DEV_TMA_MINK")) : 640;
+    if ((g.krange == KR_FULL ? g.K : g.K / 2) < min_k) return 1;
     GemmTmaArgs a;
     a.g = g;
     a.tiles_m = ceil_div(g.M, TBM);

@@ -93,6 +93,7 @@ constexpr int CTP = CT + 2;     // row stride of the staged point tiles [dim][po
                                 // dimension rows over the banks while the tile is filled (the fill walks the row-major
                                 // (point, dim) array, so consecutive threads write different dimension rows)
 constexpr int COV_THREADS = 256;
+constexpr int COV_TILES_PER_CTA = 4;
 
 // 2^(-j/32), j = 0..31, correctly rounded: the table of exp_neg_tab (staged into shared memory by the tile kernels)
 __device__ const double EXP2M_TAB[EXP_TAB] = {
@@ -215,6 +216,7 @@ struct CovArgs {
     int dist_only;  // write the distance instead of the covariance
     int vec_ok;     // 16-byte stores allowed
     int tiles_n;
+    long long ntiles;  // tiles of one matrix
 };
 
 __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
@@ -252,17 +254,26 @@ __global__ void __launch_bounds__(COV_THREADS, 4) matern_cov_kernel(const __grid
     double* xs = cov_sm;
     double* ys = cov_sm + (size_t)m.d * CTP;
     double* __restrict__ Kb = a.K + (long long)blockIdx.z * a.strideK;
+    // A CTA walks COV_TILES_PER_CTA consecutive tiles of the (row-major) tile list: the launch prologue and the
+    // x tile (same tile row) are paid once per run, and the tile index is decoded once, then stepped.
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long t_first = (long long)blockIdx.x * COV_TILES_PER_CTA;
     int ti, tj;
     if (a.mode == CM_RECT) {
-        ti = blockIdx.x / a.tiles_n;
-        tj = blockIdx.x - ti * a.tiles_n;
+        ti = (int)(t_first / a.tiles_n);
+        tj = (int)(t_first - (long long)ti * a.tiles_n);
     } else {
-        tri_decode(blockIdx.x, ti, tj);
+        tri_decode((int)t_first, ti, tj);
     }
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int r0 = ti * CT, c0 = tj * CT;
     const double pscale = a.dist_only ? 1.0 : m.c;
-    stage_points(xs, a.x + (long long)blockIdx.z * a.strideX, r0, a.n, m, tid, pscale);
+    int staged_ti = -1;
+    for (int it = 0; it < COV_TILES_PER_CTA && t_first + it < a.ntiles; ++it) {
+    const int r0 = ti * CT, c0 = tj * CT;
+    if (it > 0) __syncthreads();  // every warp is done with the previous y (and x) tile
+    if (ti != staged_ti) {
+        stage_points(xs, a.x + (long long)blockIdx.z * a.strideX, r0, a.n, m, tid, pscale);
+        staged_ti = ti;
+    }
     stage_points(ys, a.y + (long long)blockIdx.z * a.strideX, c0, a.mcols, m, tid, pscale);
     __syncthreads();
 
@@ -351,6 +362,14 @@ __global__ void __launch_bounds__(COV_THREADS, 4) matern_cov_kernel(const __grid
             }
         }
     }
+    // next tile of the list
+    if (a.mode == CM_RECT) {
+        if (++tj == a.tiles_n) { tj = 0; ++ti; }
+    } else if (++tj > ti) {
+        tj = 0;
+        ++ti;
+    }
+    }  // tile loop
 }
 
 // mdev != nullptr: batched over `batch` parameter sets living in device memory (spec then only supplies
@@ -382,7 +401,8 @@ int launch_matern_cov(const gpmp_cov_spec* spec, const MaternDev* mdev, int batc
     double bytes = mode == CM_SYM_LOWER ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
     bytes += 8.0 * (double)(n + (same ? 0 : a.mcols)) * spec->d;
     LaunchScope scope(KC_MATERN, bytes * batch, stream);
-    dim3 grid((unsigned)ntiles, 1, (unsigned)batch);
+    a.ntiles = ntiles;
+    dim3 grid((unsigned)ceil_div_ll(ntiles, COV_TILES_PER_CTA), 1, (unsigned)batch);
     const size_t cov_smem = (size_t)2 * spec->d * CTP * sizeof(double);  // x and y tiles: <= 33 KB at d = 32
     switch (dist_only ? 0 : spec->p) {
         case 0: matern_cov_kernel<0><<<grid, COV_THREADS, cov_smem, stream>>>(a); break;
@@ -444,6 +464,7 @@ __global__ void maternp_elementwise_kernel(const KernArgs a) {
 // only lower tiles are visited (off-diagonal entries weighted twice).
 // ---------------------------------------------------------------------------------------------
 constexpr int CONTRACT_MAXR = GPMP_MAX_Q + 1;
+constexpr int CONTRACT_TILES_PER_CTA = 8;
 
 struct ContractArgs {
     MaternDev m;
@@ -453,6 +474,7 @@ struct ContractArgs {
     int n, mcols, sym, same_set, tiles_n;
     int dist_only;    // vjp of the scaled distance itself: weight G_ik / h (0 at h == 0)
     int tile_off;     // sym mode: index of the first lower tile visited (row-range restricted contraction)
+    long long ntiles; // tiles visited per matrix
     double* partial;  // [nblocks][2 + d]
     // batched form (blockIdx.z = entry): per-entry kernel parameters and element strides
     const MaternDev* mdev; long long strideG, strideU, strideX;
@@ -479,20 +501,37 @@ __global__ void __launch_bounds__(COV_THREADS, 2) contract_kernel(const __grid_c
     const long long zb = blockIdx.z;
     const double* __restrict__ Gz = a.G + zb * a.strideG;
     const double* __restrict__ Uz = a.Ut ? a.Ut + zb * a.strideU : nullptr;
-    int ti, tj;
-    if (a.sym) tri_decode(blockIdx.x + a.tile_off, ti, tj);
-    else { ti = blockIdx.x / a.tiles_n; tj = blockIdx.x - ti * a.tiles_n; }
+    // A CTA walks CONTRACT_TILES_PER_CTA consecutive tiles of the tile list and keeps its running sums to itself
+    // (sK, sTr in registers, the d per-dimension sums per thread in shared memory): one block reduction and one
+    // partial record per run of tiles instead of per tile.
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
-    const int r0 = ti * CT, c0 = tj * CT;
+    double* dacc = csm + (size_t)2 * d * CTP + (size_t)2 * nr * CT;  // [d][COV_THREADS]
+    for (int j = 0; j < d; ++j) dacc[j * COV_THREADS + tid] = 0.0;
+    const long long t_first = (long long)a.tile_off + (long long)blockIdx.x * CONTRACT_TILES_PER_CTA;
+    const long long t_end = (long long)a.tile_off + a.ntiles;
+    int ti, tj;
+    if (a.sym) tri_decode((int)t_first, ti, tj);
+    else { ti = (int)(t_first / a.tiles_n); tj = (int)(t_first - (long long)ti * a.tiles_n); }
     // points pre-scaled by c / rho_j (plain 1 / rho_j for the distance vjp): the accumulated distance is t = c h,
     // and the squared differences of the second pass carry c^2, which is folded into the weights
     const double pscale = a.dist_only ? 1.0 : m.c;
     const double inv_c = 1.0 / pscale, inv_c2 = inv_c * inv_c;
-    stage_points(xs, a.x + zb * a.strideX, r0, a.n, m, tid, pscale);
+    double sK = 0.0, sTr = 0.0;
+    int staged_ti = -1;
+    for (int it = 0; it < CONTRACT_TILES_PER_CTA && t_first + it < t_end; ++it) {
+    const int r0 = ti * CT, c0 = tj * CT;
+    if (it > 0) __syncthreads();  // every warp is done with the previous tiles
+    if (ti != staged_ti) {
+        stage_points(xs, a.x + zb * a.strideX, r0, a.n, m, tid, pscale);
+        for (int e = tid; e < nr * CT; e += COV_THREADS) {
+            const int q = e / CT, i = e - q * CT;
+            ur[q][i] = r0 + i < a.n ? Uz[(long long)q * a.ldu + r0 + i] : 0.0;
+        }
+        staged_ti = ti;
+    }
     stage_points(ys, a.y + zb * a.strideX, c0, a.mcols, m, tid, pscale);
     for (int e = tid; e < nr * CT; e += COV_THREADS) {
         const int q = e / CT, i = e - q * CT;
-        ur[q][i] = r0 + i < a.n ? Uz[(long long)q * a.ldu + r0 + i] : 0.0;
         uc[q][i] = c0 + i < a.mcols ? Uz[(long long)q * a.ldu + c0 + i] : 0.0;
     }
     __syncthreads();
@@ -560,7 +599,6 @@ __global__ void __launch_bounds__(COV_THREADS, 2) contract_kernel(const __grid_c
     }
     // weights w = G_ik * sigma2 * k'(h)/h / c^2 (x2 for strictly-lower entries in sym mode)
     double w[4][4];
-    double sK = 0.0, sTr = 0.0;
     const double off_mult = a.sym ? 2.0 : 1.0;  // off-diagonal tiles of the symmetric form count twice
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -590,11 +628,7 @@ __global__ void __launch_bounds__(COV_THREADS, 2) contract_kernel(const __grid_c
             w[i][k] = mg * (dkh * inv_c2);
         }
     }
-    // per-dimension sums: warp-reduce each, lane 0 keeps the warp's running value in smem
-    {
-        double t0 = warp_sum(sK), t1 = warp_sum(sTr);
-        if (lane == 0) { wacc[warp][0] = t0; wacc[warp][1] = t1; }
-    }
+    // per-dimension sums of this tile, added to the thread's running sums
     for (int j = 0; j < d; ++j) {
         const double2 xa = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4]);
         const double2 xb = *reinterpret_cast<const double2*>(&xs[j * CTP + ty * 4 + 2]);
@@ -611,8 +645,24 @@ __global__ void __launch_bounds__(COV_THREADS, 2) contract_kernel(const __grid_c
                 s0 = fma(w[i][k], d0 * d0, s0);
                 s1 = fma(w[i][k + 1], d1 * d1, s1);
             }
-        const double s = warp_sum(s0 + s1);
-        if (lane == 0) wacc[warp][2 + j] = s;
+        dacc[j * COV_THREADS + tid] += s0 + s1;
+    }
+    // next tile of the list
+    if (a.sym) {
+        if (++tj > ti) { tj = 0; ++ti; }
+    } else if (++tj == a.tiles_n) {
+        tj = 0;
+        ++ti;
+    }
+    }  // tile loop
+    // block reduction of the 2 + d running sums (fixed order: deterministic)
+    {
+        double t0 = warp_sum(sK), t1 = warp_sum(sTr);
+        if (lane == 0) { wacc[warp][0] = t0; wacc[warp][1] = t1; }
+    }
+    for (int j = 0; j < d; ++j) {
+        const double sj = warp_sum(dacc[j * COV_THREADS + tid]);
+        if (lane == 0) wacc[warp][2 + j] = sj;
     }
     __syncthreads();
     if (tid < 2 + d) {
@@ -687,6 +737,8 @@ int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const dou
         a.tile_off = (int)((long long)tile_row0 * (tile_row0 + 1) / 2);
         nblocks = (long long)tile_row1 * (tile_row1 + 1) / 2 - a.tile_off;
     }
+    a.ntiles = nblocks;
+    nblocks = ceil_div_ll(nblocks, CONTRACT_TILES_PER_CTA);  // one CTA (and one partial record) per run of tiles
     if ((size_t)nblocks * batch * (2 + spec->d) * sizeof(double) > partial_bytes) return GPMP_ERR_WORKSPACE;
     a.partial = static_cast<double*>(partial);
     a.mdev = cb ? cb->mdev : nullptr;
@@ -695,9 +747,10 @@ int launch_contract(const gpmp_cov_spec* spec, const double* x, int n, const dou
     {
         double bytes = sym ? 8.0 * n * (n + 1.0) / 2.0 : 8.0 * (double)n * a.mcols;
         LaunchScope scope(KC_CONTRACT, bytes, stream);
-        // x / y tiles and the U rows of the tile: 2 (d + r) rows of CT doubles (<= 2 (32 + 32) 64 8 = 64 KB > 48 KB
-        // only when both d and r are near their limits: those launches opt in to the larger carve-out)
-        const size_t smem = ((size_t)2 * spec->d * CTP + (size_t)2 * (Ut ? r : 0) * CT) * sizeof(double);
+        // x / y tiles, the U rows of the tile and the per-thread running sums of the d length-scale derivatives
+        // (d x 256 doubles): 14 KB at d = 4, 28 KB at d = 8, 130 KB at the limits d = 32, r = 32 -- launches
+        // above 48 KB opt in to the larger carve-out
+        const size_t smem = ((size_t)2 * spec->d * CTP + (size_t)2 * (Ut ? r : 0) * CT + (size_t)spec->d * COV_THREADS) * sizeof(double);
         auto launch = [&](auto kern) -> int {
             if (smem > 48 * 1024 &&
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
