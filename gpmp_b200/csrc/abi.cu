@@ -430,7 +430,8 @@ int gpmp_lik_dist_group(int n, int q, void* work_dev, size_t work_bytes, int k0,
     char* base = static_cast<char*>(work_dev);
     char* pb = base + w.off_potrf;
     return dist_group((double*)(base + w.off_A), w.lda, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo),
-                      (double*)(pb + w.pw.off_tup), k0, panel_dev, info_dev, (cudaStream_t)stream);
+                      (double*)(pb + w.pw.off_tup), k0, panel_dev, info_dev, (cudaStream_t)stream,
+                      (double*)(pb + w.pw.off_tsub));
 }
 
 int gpmp_lik_dist_store(int n, int q, void* work_dev, size_t work_bytes, int k0, const double* panel_dev,

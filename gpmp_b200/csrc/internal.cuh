@@ -51,7 +51,7 @@ int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* 
                    int first_block = 0);
 
 int dist_group(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, int k0, double* panel,
-               int* info, cudaStream_t stream);
+               int* info, cudaStream_t stream, double* Tsub = nullptr);
 int dist_store(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, cudaStream_t stream);
 int dist_update(double* A, long long lda, int n, int nrows, int NB, int k0, const double* panel, int col0, int col1,
                 cudaStream_t stream);

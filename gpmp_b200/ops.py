@@ -405,51 +405,102 @@ def lik_value_dist(spec, K, x, z, P, group=None, want_grad=False):
     NB = lib().gpmp_lik_dist_block(n)
     nrows = n + q + 1
     ngroups = (n + NB - 1) // NB
-    bufs = [_empty((nrows * NB,)), _empty((nrows * NB,))]
+    # Three panel buffers in rotation and two streams per rank.  The CHAIN stream (high priority) carries what the
+    # other ranks are waiting for -- the owner's update of its next group, that group's factorisation and the start
+    # of its broadcast; the caller's stream carries the rank's bulk updates.  A latency-bound group factorisation
+    # therefore no longer holds back the owner's own trailing updates, and a panel buffer is only rewritten once
+    # the bulk updates that read it (three panels earlier) have finished.
+    NBUF = 3
+    bufs = [_empty((nrows * NB,)) for _ in range(NBUF)]
     wb = work.numel()
+    main = torch.cuda.current_stream()
+    chain = _chain_stream() if size > 1 else main
+    done_with = [None] * ngroups   # event: the bulk updates reading panel g are enqueued and finished
+    head_ready = [None] * ngroups  # event: group g has received every bulk update issued so far (through panel g - 2)
+
     def root(g):
         owner = g % size
         return td.get_global_rank(group, owner) if group is not None else owner
 
-    def bcast(g):
-        if size == 1:
-            return None
-        return td.broadcast(bufs[g & 1][: (nrows - g * NB) * NB], src=root(g), group=group, async_op=True)
+    def panel(g):
+        return bufs[g % NBUF][: (nrows - g * NB) * NB]
 
     def update(g, g2):
-        check(lib().gpmp_lik_dist_update(n, q, ptr(work), wb, g * NB, ptr(bufs[g & 1]), g2 * NB,
+        check(lib().gpmp_lik_dist_update(n, q, ptr(work), wb, g * NB, ptr(bufs[g % NBUF]), g2 * NB,
                                          min(n, (g2 + 1) * NB), stream_ptr()), "gpmp_lik_dist_update")
 
     def factor(g):
-        check(lib().gpmp_lik_dist_group(n, q, ptr(work), wb, g * NB, ptr(bufs[g & 1]), ptr(info), stream_ptr()),
+        check(lib().gpmp_lik_dist_group(n, q, ptr(work), wb, g * NB, ptr(bufs[g % NBUF]), ptr(info), stream_ptr()),
               "gpmp_lik_dist_group")
 
+    def start_broadcast(g):
+        """On the chain stream: the buffer of panel g must be free (its previous tenant, panel g - NBUF, fully
+        consumed by this rank's bulk updates), then the collective is enqueued behind the stream's work."""
+        if size == 1:
+            return None
+        if g >= NBUF and done_with[g - NBUF] is not None:
+            chain.wait_event(done_with[g - NBUF])
+        with torch.cuda.stream(chain):
+            return td.broadcast(panel(g), src=root(g), group=group, async_op=True)
+
+    chain.wait_stream(main)  # the prepared work matrix
     if rank == 0 % size:
-        factor(0)
-    pending = bcast(0)
+        with torch.cuda.stream(chain):
+            factor(0)
+    pending = start_broadcast(0)
     for g in range(ngroups):
         if pending is not None:
-            pending.wait()  # panel g has arrived (the compute stream now waits for it)
+            pending.wait()  # panel g has arrived: the caller's stream waits for it ...
+            with torch.cuda.stream(chain):
+                pending.wait()  # ... and so does the chain
+        elif size == 1:
+            pass
+        if size > 1 and rank == g % size:
+            main.wait_stream(chain)  # the owner's own factorisation produced the panel on the chain stream
         if size > 1 and rank != g % size:
-            check(lib().gpmp_lik_dist_store(n, q, ptr(work), wb, g * NB, ptr(bufs[g & 1]), stream_ptr()),
+            check(lib().gpmp_lik_dist_store(n, q, ptr(work), wb, g * NB, ptr(bufs[g % NBUF]), stream_ptr()),
                   "gpmp_lik_dist_store")
         nxt = g + 1
         if nxt < ngroups:
-            # the chain first: the owner of the next group brings it up to date, factors it and starts the
-            # broadcast; everybody else posts the receive into the other buffer and keeps updating
             if rank == nxt % size:
-                update(g, nxt)
-                factor(nxt)
-            pending = bcast(nxt)
-        for g2 in range(g + 2, ngroups):
-            if g2 % size == rank:
-                update(g, g2)
+                # the chain: bring the next group up to date, factor it, start its broadcast
+                with torch.cuda.stream(chain):
+                    if head_ready[nxt] is not None:
+                        chain.wait_event(head_ready[nxt])
+                    if g >= NBUF - 1 and done_with[nxt - NBUF] is not None:
+                        chain.wait_event(done_with[nxt - NBUF])  # factor(nxt) rewrites that buffer
+                    update(g, nxt)
+                    factor(nxt)
+            pending = start_broadcast(nxt)
+        # bulk updates of the groups this rank owns; the group the chain needs next goes first and is flagged
+        mine = [g2 for g2 in range(g + 2, ngroups) if g2 % size == rank]
+        for g2 in mine:
+            update(g, g2)
+            if g2 == g + 2:
+                head_ready[g2] = torch.cuda.Event()
+                head_ready[g2].record(main)
+        done_with[g] = torch.cuda.Event()
+        done_with[g].record(main)
+    main.wait_stream(chain)
     if size > 1:
         # a non-positive pivot is seen by the owner of its group only
         td.all_reduce(info, op=td.ReduceOp.MAX, group=group)
     check(lib().gpmp_lik_dist_finish(n, q, ptr(work), wb, ptr(out), ptr(info), stream_ptr()),
           "gpmp_lik_dist_finish")
     return FitState(work, n, q, d, spec, x, want_grad), out
+
+
+_chain_streams = {}
+
+
+def _chain_stream():
+    """High-priority stream of the current device for the critical path of the partitioned factorisation."""
+    dev = torch.cuda.current_device()
+    st = _chain_streams.get(dev)
+    if st is None:
+        st = torch.cuda.Stream(device=dev, priority=-1)
+        _chain_streams[dev] = st
+    return st
 
 
 def _ws_matrix(state, which):
