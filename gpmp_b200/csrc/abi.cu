@@ -333,6 +333,8 @@ int gpmp_transpose(const double* in_dev, long long ldi, double* out_dev, long lo
 }
 
 // development hook: phase timestamps (clock64) of the diagonal-tile kernel; not declared in the header
+// development hook: phase clocks of the last stamped chain-step launch (GPMP_DEV_STAMPS=1), 64 values
+int gpmp_debug_chain_stamps(long long* out_host) { return debug_chain_stamps(out_host); }
 int gpmp_debug_potf2(double* A_dev, long long lda, int nb, double* Tlo_dev, double* Tup_dev, int* info_dev,
                      long long* clocks_dev, void* stream) {
     return debug_potf2(A_dev, lda, nb, Tlo_dev, Tup_dev, info_dev, clocks_dev, (cudaStream_t)stream);

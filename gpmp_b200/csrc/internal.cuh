@@ -57,6 +57,7 @@ int dist_update(double* A, long long lda, int n, int nrows, int NB, int k0, cons
                 cudaStream_t stream);
 int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo, double* Tup, double* scratch,
                 int* info, cudaStream_t stream);
+int debug_chain_stamps(long long* out);
 int debug_potf2(double* A, long long lda, int nb, double* Tlo, double* Tup, int* info, long long* dbg,
                 cudaStream_t stream);
 

@@ -555,47 +555,24 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_kernel(const Potf2Args
 }
 
 
-// ---- factor-only tile kernel (the chain's and the batched sweeps' version) ----------------------------------
-// Same arithmetic as potf2_kernel in POTF2_FACTOR mode (factor + the four 32x32 diagonal-block inverses), but
-// the tile is kept packed (lower block rows only, 84 KB) and the CTA has 8 warps, so two tiles share an SM:
-// a batched sweep overlaps the serial pivot chain of one tile with the tensor-pipe phases of the other.
 constexpr int PF_THREADS = 256;
 constexpr int PF_XLD = 20;
 constexpr int PF_SMEM = (TS_LP + 4 * 16 * PF_XLD + PT) * 8;
 
-__global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2Args a) {
-    extern __shared__ __align__(16) double sm[];
-    double* S = sm;                       // packed tile: lower = L, strict upper of the diagonal blocks = T_bb^T
-    double* X = sm + TS_LP;               // per-warp 16 x 16 scratch of the block inversion
-    double* rinv = X + 4 * 16 * PF_XLD;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PF_THREADS / 32;
-    const long long zb = blockIdx.x;
-    double* __restrict__ A = a.A + zb * a.strideA;
-    const int nb = a.nb;
-    {
-        const uint32_t sb = smem_u32(S);
-        for (int e = tid; e < PT * (PT / 2); e += PF_THREADS) {
-            const int r = e >> 6, c = (e & 63) * 2;  // chunk of two columns
-            if (c > r) continue;
-            int bytes = 0;
-            if (r < nb) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
-            const double* src = bytes ? A + (long long)r * a.lda + c : A;
-            cp_async16(sb + (uint32_t)pk(r, c) * 8u, src, bytes);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        // strict upper part of the diagonal blocks (the chunk holding the diagonal keeps its first entry)
-        for (int e = tid; e < PT * 16; e += PF_THREADS) {
-            const int r = e >> 4, c = (r & ~31) + (e & 15) * 2;
-            if (c + 1 <= r) continue;
-            if (c > r) S[pk(r, c)] = 0.0;
-            S[pk(r, c + 1)] = 0.0;
-        }
-        if (tid >= nb && tid < PT) S[pk(tid, tid)] = 1.0;
-    }
-    __syncthreads();
-
+// Factorisation of a packed 128x128 tile resident in shared memory (S: packed layout pk(r, c), lower part = the
+// matrix, strict upper part of the diagonal 32-blocks zero, dead rows padded with identity): on return the lower
+// part holds L, the strict upper part of the diagonal blocks T_bb^T (the 32x32 block inverses) and rinv 1 / diag(L).
+// X: 4 x 16 x PF_XLD doubles of scratch.  All NT threads of the CTA must call it; bad_out (written by thread 0
+// only) is the 1-based local index of the first non-positive pivot, 0 if none.
+// `pre(jb, w, nw)` is run by the nw look-ahead warps (index w) at the start of the diagonal phase of panel jb, before
+// their share of the previous panel's trailing update: the fused chain step finishes the tile's own K = 128 update
+// there, one column block ahead of the factorisation.
+struct NoPre {
+    __device__ __forceinline__ void operator()(int, int, int) const {}
+};
+template <int NT, class Pre = NoPre>
+__device__ __forceinline__ void factor_packed(double* S, double* X, double* rinv, int& bad_out, Pre pre = Pre()) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT / 32;
     int bad = 0;  // 1-based local index of the first non-positive pivot (warp 0, lane 0 only)
     for (int jb = 0; jb < 4; ++jb) {
         const int c0 = jb * 32, ldd = ts_ld(jb);
@@ -604,12 +581,14 @@ __global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2
             diag32_factor<true>(D, ldd, rinv + c0, c0, bad);
         } else if (warp == 1) {
             diag32_factor<false>(D, ldd, rinv + c0, c0, bad);
-        } else if (jb > 0 && (warp & 3)) {
+        } else if (warp & 3) {
             // look-ahead: the other warps finish the previous panel's trailing update (everything but this
             // diagonal block, updated first) while warps 0 and 1 walk the pivot chain (warp 4 shares warp 0's
             // scheduler partition and FP64 pipe: it stays out)
-            syrk32_rows(4, (PT - c0) / 8, warp - 2 - (warp >> 2), nwarps - nwarps / 4 - 1,
-                        [&](int r) { return S + pk(c0 + r, c0 - 32); }, [&](int r) { return S + pk(c0 + r, c0); });
+            pre(jb, warp - 2 - (warp >> 2), nwarps - nwarps / 4 - 1);
+            if (jb > 0)
+                syrk32_rows(4, (PT - c0) / 8, warp - 2 - (warp >> 2), nwarps - nwarps / 4 - 1,
+                            [&](int r) { return S + pk(c0 + r, c0 - 32); }, [&](int r) { return S + pk(c0 + r, c0); });
         }
         __syncthreads();
         const int rb = c0 + 32;       // first row below the diagonal block
@@ -637,10 +616,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2
             __syncthreads();
         }
     }
-    if (warp == 0 && lane == 0 && bad && a.info) {
-        int* ip = a.info + zb * a.strideInfo;
-        atomicCAS(ip, 0, a.row0 + bad);
-    }
+    if (warp == 0 && lane == 0) bad_out = bad;
 
     // ---- inverse of the four 32x32 diagonal blocks, one warp each: 8x8 in registers, then 8 -> 16 -> 32 ---
     if (warp < 4) {
@@ -715,6 +691,52 @@ __global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2
             });
     }
     __syncthreads();
+}
+
+// ---- factor-only tile kernel (the chain's and the batched sweeps' version) ----------------------------------
+// Same arithmetic as potf2_kernel in POTF2_FACTOR mode (factor + the four 32x32 diagonal-block inverses), but
+// the tile is kept packed (lower block rows only, 84 KB) and the CTA has 8 warps, so two tiles share an SM:
+// a batched sweep overlaps the serial pivot chain of one tile with the tensor-pipe phases of the other.
+
+__global__ void __launch_bounds__(PF_THREADS, 2) potf2_factor_kernel(const Potf2Args a) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                       // packed tile: lower = L, strict upper of the diagonal blocks = T_bb^T
+    double* X = sm + TS_LP;               // per-warp 16 x 16 scratch of the block inversion
+    double* rinv = X + 4 * 16 * PF_XLD;
+    const int tid = threadIdx.x;
+    const long long zb = blockIdx.x;
+    double* __restrict__ A = a.A + zb * a.strideA;
+    const int nb = a.nb;
+    {
+        const uint32_t sb = smem_u32(S);
+        for (int e = tid; e < PT * (PT / 2); e += PF_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;  // chunk of two columns
+            if (c > r) continue;
+            int bytes = 0;
+            if (r < nb) bytes = (c + 1 < nb) ? 16 : (c < nb ? 8 : 0);
+            const double* src = bytes ? A + (long long)r * a.lda + c : A;
+            cp_async16(sb + (uint32_t)pk(r, c) * 8u, src, bytes);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // strict upper part of the diagonal blocks (the chunk holding the diagonal keeps its first entry)
+        for (int e = tid; e < PT * 16; e += PF_THREADS) {
+            const int r = e >> 4, c = (r & ~31) + (e & 15) * 2;
+            if (c + 1 <= r) continue;
+            if (c > r) S[pk(r, c)] = 0.0;
+            S[pk(r, c + 1)] = 0.0;
+        }
+        if (tid >= nb && tid < PT) S[pk(tid, tid)] = 1.0;
+    }
+    __syncthreads();
+
+    int bad = 0;  // 1-based local index of the first non-positive pivot (thread 0 only)
+    factor_packed<PF_THREADS>(S, X, rinv, bad);
+    if (tid == 0 && bad && a.info) {
+        int* ip = a.info + zb * a.strideInfo;
+        atomicCAS(ip, 0, a.row0 + bad);
+    }
 
     // ---- write back: L (lower, zero upper) into A; the diagonal blocks of T into Tlo ------------------------
     const bool vec = ((a.lda & 1) == 0) && ((a.ldt & 1) == 0);
@@ -1049,6 +1071,442 @@ static int launch_trsm_tile(TrsmTileArgs a, int batch, cudaStream_t stream) {
     return GPMP_OK;
 }
 
+// ---- fused chain step: one launch per 128-column step of a column group -------------------------------------------
+// For the factored tile k (columns [col, col + 128), factor and 32x32 block inverses already in place) one launch
+// does the whole right-looking step inside the group:
+//   solve     X = P L_k^-T for every row below the tile (blocked substitution, as trsm_tile_kernel), written into A
+//             in place and mirrored into the upper tiles;
+//   update    the `nrem` 128-column blocks that remain in the group receive -X X_j^T (K = 128, lower 8x8 tiles
+//             only), X_j = the solved rows of tile j's own row block;
+//   factor    tile k + 1 is factored (factor + 32x32 block inverses, packed in shared memory) as soon as its own 128
+//             rows are solved and its diagonal tile is updated.
+// CTA 0 (the "narrow" CTA) owns the rows of tile k + 1: it solves them, publishes them, applies the K = 128 update to
+// the diagonal tile from shared memory and factors it -- the only serial dependency between two steps.  The other
+// ("wide") CTAs take 64 rows each from the rows below; the ones whose rows are row blocks of the group's later
+// tiles publish their solved rows too.  A consumer waits for a producer through a flag in global memory
+// (st.release / ld.acquire, gpu scope); producers are always CTAs with a lower block index than any CTA that can
+// be left waiting for an SM (indices 0 .. 2 nrem - 2), so the waits cannot deadlock.
+// Replaces, per step, the tile kernel + the panel solve + the in-group K = 128 GEMMs (3-4 dependent launches).
+struct ChainStepArgs {
+    double* A; long long lda;
+    int n, nrows;            // order of the matrix; rows including the extra (whitening) rows below it
+    int col;                 // first column of tile k
+    int nrem;                // full 128-column tiles of the group after tile k (0: solve only)
+    const double* Tsub_k;    // 128 x 128 (ld 128): the 32x32 diagonal-block inverses of tile k
+    double* Tsub_next;       // out: the same for tile k + 1 (nrem >= 1)
+    int* info;
+    unsigned int* flags;     // ring of CS_FLAGS words
+    unsigned int flag_id;    // producer p publishes flags[(flag_id + p) & (CS_FLAGS - 1)] = flag_id + p
+    int stamps;              // development: the narrow CTA and wide CTA 0 record phase clocks
+};
+constexpr int CS_THREADS = 512;
+constexpr int CS_FLAGS = 1 << 16;
+constexpr int CS_SMEM = (TS_LP + PT * TS_LD + PT) * 8;
+__device__ unsigned int g_chain_flags[CS_FLAGS];
+__device__ long long g_cs_stamps[64];  // development: clock64() at the phase boundaries of the last stamped launch
+#define CS_STAMP(i)                                                 \
+    do {                                                            \
+        if (stamp_base >= 0 && threadIdx.x == 0) g_cs_stamps[stamp_base + (i)] = clock64(); \
+    } while (0)
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// -x through the integer pipe (the FP64 pipe is the one the DMMAs need)
+__device__ __forceinline__ double flip_sign(double x) {
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
+// X = R L^-T for one 8-row strip (lane row xrow: A-fragment row and C row), in place; Lp = the packed operand
+// (L_bc below the diagonal blocks, T_bb on them) -- the substitution of trsm_tile_kernel
+__device__ __forceinline__ void solve_strip_packed(const double* Lp, double* xrow) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, kk = lane & 3;
+    for (int b = 0; b < 4; ++b) {
+        const int cb = 32 * b, ldb = ts_ld(b);
+        const double* Lb = Lp + ts_base(b) + gq * ldb + kk;
+        double acc[4][2];
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) acc[j8][0] = acc[j8][1] = 0.0;
+        for (int k0 = 0; k0 < cb; k0 += 32) {
+            double av[8], bv[8][4];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                av[s] = xrow[k0 + 4 * s + kk];
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) bv[s][j8] = Lb[8 * j8 * ldb + k0 + 4 * s];
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) dmma884(acc[j8][0], acc[j8][1], av[s], bv[s][j8]);
+        }
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+            xrow[cb + 8 * j8 + 2 * kk] -= acc[j8][0];
+            xrow[cb + 8 * j8 + 2 * kk + 1] -= acc[j8][1];
+            acc[j8][0] = acc[j8][1] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const double av = xrow[cb + 4 * s + kk];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8)
+                if (s < 2 * (j8 + 1)) dmma884(acc[j8][0], acc[j8][1], av, Lb[8 * j8 * ldb + cb + 4 * s]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+            xrow[cb + 8 * j8 + 2 * kk] = acc[j8][0];
+            xrow[cb + 8 * j8 + 2 * kk + 1] = acc[j8][1];
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(CS_THREADS, 1) chain_step_kernel(const ChainStepArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double* Lp = sm;                 // packed operand of the solve; later: B rows (wide) / the packed next tile (narrow)
+    double* Xs = sm + TS_LP;         // [128][TS_LD]: the solved rows; wide CTAs use rows 0..63, rows 64.. hold B rows
+    double* rinv = Xs + PT * TS_LD;  // [128]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, kk = lane & 3;
+    const long long lda = a.lda;
+    double* A = a.A;
+    const int col = a.col, rb = col + PT;
+    const bool has_narrow = a.nrem >= 1;
+    const bool narrow = has_narrow && blockIdx.x == 0;
+    if (has_narrow && blockIdx.x == gridDim.x - 1) {
+        // last CTA: the mirrored upper tile of the narrow CTA's rows (off the chain: nothing in this launch reads it)
+        if (tid == 0) {
+            const unsigned int* f = a.flags + (a.flag_id & (CS_FLAGS - 1));
+            while (ld_acquire_u32(f) != a.flag_id) __nanosleep(256);
+        }
+        __syncthreads();
+        const uint32_t xb = smem_u32(Xs);
+        const double* P = A + (long long)rb * lda + col;
+        for (int e = tid; e < PT * (PT / 2); e += CS_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            cp_async16(xb + (uint32_t)(r * TS_LD + c) * 8u, P + (long long)r * lda + c, 16);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int e = tid; e < PT * PT; e += CS_THREADS) {
+            const int j = e >> 7, r = e & (PT - 1);
+            A[(long long)(col + j) * lda + rb + r] = Xs[r * TS_LD + j];
+        }
+        return;
+    }
+    const int wb = (int)blockIdx.x - (has_narrow ? 1 : 0);               // wide block index
+    const int r0 = narrow ? rb : (has_narrow ? rb + PT : rb) + 64 * wb;  // first global row of this CTA
+    const int R = narrow ? PT : 64;
+    const int live = min(R, a.nrows - r0);                               // rows that exist
+    if (live <= 0) return;
+    const int stamp_base = a.stamps ? (narrow ? 0 : (wb == 0 ? 16 : -1)) : -1;
+    CS_STAMP(0);
+
+    // ---- stage the operand tile (packed) and this CTA's rows ---------------------------------------------------
+    {
+        const double* Lt = A + (long long)col * (lda + 1);
+        const uint32_t lb = smem_u32(Lp);
+        for (int e = tid; e < PT * (PT / 2); e += CS_THREADS) {
+            const int i = e >> 6, c = (e & 63) * 2;
+            const int b = i >> 5;
+            if (c >= 32 * (b + 1)) continue;
+            const bool diag_blk = (c >> 5) == b;
+            const double* src = diag_blk ? a.Tsub_k + (long long)i * PT + c : Lt + (long long)i * lda + c;
+            cp_async16(lb + (uint32_t)(ts_base(b) + (i - 32 * b) * ts_ld(b) + c) * 8u, src, 16);
+        }
+        const uint32_t xb = smem_u32(Xs);
+        const double* P = A + (long long)r0 * lda + col;
+        for (int e = tid; e < R * (PT / 2); e += CS_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            const bool on = r < live;
+            cp_async16(xb + (uint32_t)(r * TS_LD + c) * 8u, on ? P + (long long)r * lda + c : P, on ? 16 : 0);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    CS_STAMP(1);
+    // ---- solve: one 8-row strip per warp -------------------------------------------------------------------------
+    if (warp * 8 < R) solve_strip_packed(Lp, Xs + (warp * 8 + gq) * TS_LD);
+
+    if (narrow) {
+        // The diagonal tile's own update, C - X X^T, in units of 2 x 2 8x8 tiles (16 x 16 entries, one warp each; the
+        // 36 lower units of the 8 x 8 unit grid).  Only the first 32 columns (15 units) are needed before the
+        // factorisation starts; the units of columns 32..63 (11) and 64..127 (10) are computed by the look-ahead warps
+        // of the tile factorisation under the pivot chains of its first and second panel.
+        const double* Cd = A + (long long)rb * (lda + 1);
+        double* S = Lp;  // the packed tile takes the place of the solve's operand
+        auto unit_load = [&](int ui, int uj, double (&acc)[2][2][2]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(Cd + (long long)((2 * ui + i) * 8 + gq) * lda +
+                                                                        (2 * uj + j) * 8 + 2 * kk);
+                    acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+                }
+        };
+        auto unit_run = [&](int ui, int uj, double (&acc)[2][2][2]) {
+            const double* ap = Xs + (16 * ui + gq) * TS_LD + kk;
+            const double* bp = Xs + (16 * uj + gq) * TS_LD + kk;
+            for (int k0 = 0; k0 < PT; k0 += 32) {
+                double fa[2][8], fb[2][8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        fa[i][s] = flip_sign(ap[8 * i * TS_LD + k0 + 4 * s]);
+                        fb[i][s] = bp[8 * i * TS_LD + k0 + 4 * s];
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i][s], fb[j][s]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = (2 * ui + i) * 8 + gq, c = (2 * uj + j) * 8 + 2 * kk;
+                    if (c <= r) S[pk(r, c)] = acc[i][j][0];
+                    if (c + 1 <= r) S[pk(r, c + 1)] = acc[i][j][1];
+                }
+        };
+        // first 32 columns: units (ui, 0), ui = 0..7 -> warps 0..7; (ui, 1), ui = 1..7 -> warps 8..14
+        const bool u_on = warp < 15;
+        const int u_i = warp < 8 ? warp : warp - 7, u_j = warp < 8 ? 0 : 1;
+        double acc0[2][2][2];
+        if (u_on) unit_load(u_i, u_j, acc0);  // (the latency hides under the write-out)
+        __syncthreads();  // every strip is solved
+        CS_STAMP(2);
+        // publish the solved rows: A in place (the mirrored upper tile is written by the last CTA of the grid)
+        for (int e = tid; e < PT * (PT / 2); e += CS_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            *reinterpret_cast<double2*>(A + (long long)(rb + r) * lda + col + c) =
+                make_double2(Xs[r * TS_LD + c], Xs[r * TS_LD + c + 1]);
+        }
+        __syncthreads();  // the solve's operand in Lp is dead from here on: the units write the packed tile there
+        if (u_on) unit_run(u_i, u_j, acc0);
+        // the stores above have long left by now: the fence is cheap here, and the wide CTAs have slack
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_u32(a.flags + (a.flag_id & (CS_FLAGS - 1)), a.flag_id);
+        CS_STAMP(3);
+        // strict upper part of the diagonal 32-blocks: zero (as the packed tile kernel expects)
+        for (int e = tid; e < PT * 32; e += CS_THREADS) {
+            const int r = e >> 5, c = (r & ~31) + (e & 31);
+            if (c > r) S[pk(r, c)] = 0.0;
+        }
+        __syncthreads();
+        CS_STAMP(4);
+        int bad = 0;
+        factor_packed<CS_THREADS>(S, Xs + PT * TS_LD - 4 * 16 * PF_XLD, rinv, bad, [&](int jb, int w, int nw) {
+            // columns 32..63 under the first pivot chain: units (ui, 2), ui = 2..7, (ui, 3), ui = 3..7 (11 = nw);
+            // columns 64..127 under the second: (ui, uj), 4 <= uj <= ui <= 7 (10)
+            if (jb > 1) return;
+            int ui = -1, uj = 0;
+            if (jb == 0) {
+                if (w < 6) { ui = 2 + w; uj = 2; }
+                else if (w < 11) { ui = w - 3; uj = 3; }
+            } else if (w < 10) {
+                uj = w < 4 ? 4 : (w < 7 ? 5 : (w < 9 ? 6 : 7));
+                ui = uj + w - (uj == 4 ? 0 : (uj == 5 ? 4 : (uj == 6 ? 7 : 9)));
+            }
+            if (ui >= 0) {
+                double acc[2][2][2];
+                unit_load(ui, uj, acc);
+                unit_run(ui, uj, acc);
+            }
+            // the previous panel's trailing update (next in this phase) reads what the units above wrote
+            if (jb == 1) asm volatile("bar.sync 3, %0;" ::"r"(32 * nw) : "memory");
+        });
+        CS_STAMP(6);
+        if (tid == 0 && bad && a.info) atomicCAS(a.info, 0, rb + bad);
+        double* An = A + (long long)rb * (lda + 1);
+        for (int e = tid; e < PT * (PT / 2); e += CS_THREADS) {
+            const int r = e >> 6, c = (e & 63) * 2;
+            const double l0 = c <= r ? S[pk(r, c)] : 0.0;
+            const double l1 = c + 1 <= r ? S[pk(r, c + 1)] : 0.0;
+            *reinterpret_cast<double2*>(An + (long long)r * lda + c) = make_double2(l0, l1);
+            if ((r >> 5) == (c >> 5)) {
+                const double t0 = r > c ? S[pk(c, r)] : (r == c ? rinv[r] : 0.0);
+                const double t1 = r > c + 1 ? S[pk(c + 1, r)] : (r == c + 1 ? rinv[r] : 0.0);
+                *reinterpret_cast<double2*>(a.Tsub_next + (long long)r * PT + c) = make_double2(t0, t1);
+            }
+        }
+        CS_STAMP(7);
+        return;
+    }
+
+    // ---- wide CTA ------------------------------------------------------------------------------------------------
+    __syncthreads();
+    CS_STAMP(2);
+    for (int e = tid; e < 64 * (PT / 2); e += CS_THREADS) {
+        const int r = e >> 6, c = (e & 63) * 2;
+        if (r < live)
+            *reinterpret_cast<double2*>(A + (long long)(r0 + r) * lda + col + c) =
+                make_double2(Xs[r * TS_LD + c], Xs[r * TS_LD + c + 1]);
+    }
+    if (r0 < a.n) {
+        const int mlive = min(live, a.n - r0);  // only rows of the matrix itself have a mirrored tile
+        for (int e = tid; e < PT * 64; e += CS_THREADS) {
+            const int j = e >> 6, r = e & 63;
+            if (r < mlive) A[(long long)(col + j) * lda + r0 + r] = Xs[r * TS_LD + j];
+        }
+    }
+    const int gend = rb + PT * a.nrem;  // first row below the group's own row blocks
+    if (r0 < gend) {
+        // this CTA's rows belong to a later tile of the group: others read them as the B operand of that tile's block
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int id = a.flag_id + 1u + (unsigned int)wb;
+            st_release_u32(a.flags + (id & (CS_FLAGS - 1)), id);
+        }
+    }
+    // updates of the group's remaining column blocks: block t (columns cj = col + 128 t) needs the solved rows
+    // [cj, cj + 128) as B, in halves of 64 rows: half 0 -> the Lp region, half 1 -> rows 64.. of Xs
+    CS_STAMP(3);
+    double* Bh[2] = {Lp, Xs + 64 * TS_LD};
+    const int wi = warp & 3, wj = warp >> 2;  // warp tile: rows 16 wi .., columns 32 wj .. of the 64 x 128 block
+    for (int t = 1; t <= a.nrem; ++t) {
+        const int cj = col + PT * t;
+        if (cj > r0 + live - 1) break;  // this block lies right of the CTA's rows entirely
+        const int nh = (cj + 64 <= r0 + live - 1) ? 2 : 1;  // halves with columns <= the last row
+        __syncthreads();  // previous users of the B buffers (the solve / the previous block) are done
+        if (tid == 0) {
+            for (int h = 0; h < nh; ++h) {
+                const unsigned int id = a.flag_id + (t == 1 ? 0u : 1u + 2u * (unsigned int)(t - 2) + (unsigned int)h);
+                const unsigned int* f = a.flags + (id & (CS_FLAGS - 1));
+                while (ld_acquire_u32(f) != id) __nanosleep(64);
+                if (t == 1) break;  // tile k + 1's rows are one producer
+            }
+        }
+        __syncthreads();
+        for (int h = 0; h < nh; ++h) {
+            const uint32_t bb = smem_u32(Bh[h]);
+            const double* src = A + (long long)(cj + 64 * h) * lda + col;
+            for (int e = tid; e < 64 * (PT / 2); e += CS_THREADS) {
+                const int r = e >> 6, c = (e & 63) * 2;
+                cp_async16(bb + (uint32_t)(r * TS_LD + c) * 8u, src + (long long)r * lda + c, 16);
+            }
+        }
+        cp_async_commit();
+        CS_STAMP(1 + 3 * t);
+        // C values of the warp's 2 x 4 tiles while the B rows arrive
+        const int h = wj >> 1;  // half the warp's columns fall in
+        const bool active = h < nh;
+        double acc[2][4][2];
+        double* Cb = A + (long long)r0 * lda + cj;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = 16 * wi + 8 * i + gq, c = 32 * wj + 8 * j + 2 * kk;
+                acc[i][j][0] = acc[i][j][1] = 0.0;
+                if (active && r < live && cj + c <= r0 + r) {
+                    const double2 v = *reinterpret_cast<const double2*>(Cb + (long long)r * lda + c);
+                    acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+                }
+            }
+        cp_async_wait<0>();
+        __syncthreads();
+        CS_STAMP(2 + 3 * t);
+        if (active) {
+            const double* Bp = Bh[h] + (32 * (wj & 1) + gq) * TS_LD + kk;
+            const double* Ap = Xs + (16 * wi + gq) * TS_LD + kk;
+            for (int k0 = 0; k0 < PT; k0 += 32) {
+                double fa[2][8], fb[4][8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) fa[i][s] = flip_sign(Ap[8 * i * TS_LD + k0 + 4 * s]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) fb[j][s] = Bp[8 * j * TS_LD + k0 + 4 * s];
+                }
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i][s], fb[j][s]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = 16 * wi + 8 * i + gq, c = 32 * wj + 8 * j + 2 * kk;
+                    // 8x8 tiles that reach above the diagonal keep their upper entries untouched
+                    if (r < live && cj + c <= r0 + r) {
+                        if (cj + c + 1 <= r0 + r)
+                            *reinterpret_cast<double2*>(Cb + (long long)r * lda + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        else
+                            Cb[(long long)r * lda + c] = acc[i][j][0];
+                    }
+                }
+        }
+        CS_STAMP(3 + 3 * t);
+    }
+}
+
+static unsigned int chain_flag_base(unsigned int count) {
+    static std::mutex m;
+    static unsigned int next = 1;
+    std::lock_guard<std::mutex> lock(m);
+    const unsigned int b = next;
+    next += count;
+    if (next < b) next = 1 + count;  // (wrap-around: ids only need to differ from what a slot last held)
+    return b;
+}
+
+static int dev_env(const char* name);
+// development hook (not part of the C-ABI header): the phase clocks of the last stamped chain-step launch
+int debug_chain_stamps(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_cs_stamps, sizeof(long long) * 64) == cudaSuccess ? GPMP_OK : GPMP_ERR_CUDA;
+}
+
+static int launch_chain_step(ChainStepArgs a, cudaStream_t stream) {
+    static unsigned long long configured = 0;
+    static unsigned int* flags_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
+        if (cudaFuncSetAttribute(chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM) != cudaSuccess)
+            return GPMP_ERR_CUDA;
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_chain_flags) != cudaSuccess) return GPMP_ERR_CUDA;
+        flags_dev[dev & 63] = static_cast<unsigned int*>(p);
+        configured |= 1ull << (dev & 63);
+    }
+    a.flags = flags_dev[dev & 63];
+    static const bool stamps = dev_env("GPMP_DEV_STAMPS") != 0;
+    a.stamps = stamps ? 1 : 0;
+    const bool has_narrow = a.nrem >= 1;
+    const int rb = a.col + PT;
+    const int wide_rows = a.nrows - (has_narrow ? rb + PT : rb);
+    const int nwide = wide_rows > 0 ? ceil_div(wide_rows, 64) : 0;
+    const int grid = (has_narrow ? 2 : 0) + nwide;  // narrow CTA first, the mirror CTA of its rows last
+    if (grid <= 0) return GPMP_OK;
+    const double M = (double)(a.nrows - rb);
+    LaunchScope scope(KC_GEMM, 2.0 * M * PT * PT * (1.0 + a.nrem), stream);
+    chain_step_kernel<<<grid, CS_THREADS, CS_SMEM, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
 // ---- panel copy-back: W (rows x nb, ld ldw) -> A panel (lower) and its mirror in the upper tiles --
 struct CopyPanelArgs {
     const double* W; long long ldw; long long strideW;
@@ -1220,6 +1678,16 @@ static int tile_step_chain(const PotrfCtx& c, int k0, int j0, double* Wg, long l
     return launch_trsm_tile(t, c.batch, stream);
 }
 
+// Factor-only tile kernel for the first tile of the group starting at k0 (the fused chain steps do the rest).
+static int tile_factor_chain(const PotrfCtx& c, int k0, cudaStream_t stream) {
+    Potf2Args pa;
+    pa.A = c.A + (long long)k0 * (c.lda + 1); pa.lda = c.lda; pa.strideA = c.strideA;
+    pa.Tlo = c.Tsub + (long long)(k0 / PT) * PT * PT; pa.Tup = nullptr; pa.ldt = PT; pa.strideT = c.strideTsub;
+    pa.nb = min(PT, c.n - k0); pa.info = c.info; pa.strideInfo = c.strideInfo; pa.row0 = k0; pa.dbg = nullptr;
+    pa.mode = POTF2_FACTOR;
+    return launch_potf2(pa, 1, stream);
+}
+
 // 128-wide inverse of the tile at column `col` from its factor (off the chain).
 static int tile_inverse(const PotrfCtx& c, int k0, int j0, cudaStream_t stream) {
     const int NB = c.NB, gw = min(NB, c.n - k0);
@@ -1323,10 +1791,9 @@ static int trailing_update(const PotrfCtx& c, int k, const double* Pnl, long lon
 // caller streams that factor concurrently never share chain streams or reuse each other's events (the ABI is
 // re-entrant per (stream, workspace)).  The sets live for the life of the process.
 constexpr int LA_DEPTH = 4;    // deepest look-ahead the stream / event sets are sized for
-constexpr int LA_DEFAULT = 1;  // depth used: measured at n = 8192 (value, ms): depth 1 8.96, 2 9.10, 4 9.17 -- under a
-                               // running bulk update the chain's whole-SM kernels (tile kernel 133 KB, panel solve
-                               // 229 KB of shared memory) wait for SMs to drain, so the chain is slower than the bulk
-                               // even while the trailing matrix is large and a deeper window has no lead to bank
+constexpr int LA_DEFAULT = 4;  // depth used: measured at n = 8192 with the fused chain step (value, ms): depth 1 8.82,
+                               // 2 8.81, 3 8.54, 4 8.47 (with three chain launches per step the chain was the slower
+                               // side under a running bulk update at every depth: 8.96 / 9.10 / - / 9.17)
 struct LookAhead {
     cudaStream_t caller = nullptr;
     int dev = -1;
@@ -1427,8 +1894,37 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
     auto ev = [&](int g, int i) { return la->ev[4 + 2 * LA_DEPTH + g * EV + i]; };  // g = 0 .. nblk + D
     enum { E_PANEL = 0, E_REST = 1, E_HEADREST = 2, E_TRSM = 3 /* +c, c<4 */, E_IN = 7 /* +c, c<2 */, E_G2 = 9 };
     // steps of the group starting at k0 (group index g); head_rest: wait for the helper's head update first
+    static const bool no_fuse = dev_env("GPMP_DEV_NOFUSE") != 0;
     auto run_group = [&](int g, int k0, double* Wn, bool head_rest) -> int {
         const int gw = min(NB, n - k0), nblocks = ceil_div(gw, PT);
+        if (!no_fuse && gw % PT == 0) {
+            // groups of full tiles: the first tile on its own (its columns were completed by the head update on
+            // this stream), then ONE fused launch per step -- solve below tile cb, every in-group update of the step,
+            // factorisation of tile cb + 1 (chain_step_kernel).  The in-group updates write the group's remaining
+            // columns, so the first step follows the helper's part of the head update.
+            int rc2 = tile_factor_chain(c, k0, B);
+            if (rc2) return rc2;
+            const unsigned int fid = chain_flag_base(8u * (unsigned int)nblocks);
+            for (int cb = 0; cb < nblocks; ++cb) {
+                const int col = k0 + cb * PT;
+                if (cb == 0 && head_rest) cudaStreamWaitEvent(B, ev(g, E_HEADREST), 0);
+                ChainStepArgs cs;
+                cs.A = c.A; cs.lda = c.lda; cs.n = c.n; cs.nrows = c.nrows; cs.col = col;
+                cs.nrem = nblocks - 1 - cb;
+                cs.Tsub_k = c.Tsub + (long long)(col / PT) * PT * PT;
+                cs.Tsub_next = c.Tsub + (long long)(col / PT + 1) * PT * PT;
+                cs.info = c.info; cs.flags = nullptr; cs.flag_id = fid + 8u * (unsigned int)cb;
+                rc2 = launch_chain_step(cs, B);
+                if (rc2) return rc2;
+                cudaEventRecord(ev(g, E_TRSM + cb), B);
+                // the 128-wide inverse of the tile is needed only after the factorisation: helper stream
+                cudaStreamWaitEvent(H, ev(g, E_TRSM + cb), 0);
+                rc2 = tile_inverse(c, k0, cb * PT, H);
+                if (rc2) return rc2;
+            }
+            cudaEventRecord(ev(g, E_PANEL), B);
+            return GPMP_OK;
+        }
         for (int cb = 0; cb < nblocks; ++cb) {
             const int j0 = cb * PT;
             int rc2 = tile_step_chain(c, k0, j0, Wn, strideW, B);
