@@ -59,6 +59,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void decode_tile_sq(const GemmTmaArgs& a, int t, int& ti, int& tj) {
     if (!a.g.lower) {
         ti = t / a.tiles_n;
@@ -122,8 +129,14 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const uint32_t fb = bar_full + 8 * s;
         mbar_arm(fb, T_STAGE_BYTES);
         const int kc = k0 + chunk * TBK;
-        tma_load_2d(st, &mapA, kc, m0, fb);
-        tma_load_2d(st + T_A_BYTES, &mapB, kc, n0, fb);
+        if (g.batch2 > 1) {
+            // second batch level (the block pairs of one level of the triangular inverse): third map coordinate
+            tma_load_3d(st, &mapA, kc, m0, (int)blockIdx.y, fb);
+            tma_load_3d(st + T_A_BYTES, &mapB, kc, n0, (int)blockIdx.y, fb);
+        } else {
+            tma_load_2d(st, &mapA, kc, m0, fb);
+            tma_load_2d(st + T_A_BYTES, &mapB, kc, n0, fb);
+        }
     };
     if (tid == 0) {
         const int pre = nk < TSTAGES ? nk : TSTAGES;
@@ -181,8 +194,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     // epilogue (same as gemm.cu)
     const double alpha = g.alpha, beta = g.beta;
-    double* __restrict__ C = g.C;
-    double* __restrict__ Ct = g.Ct;
+    double* __restrict__ C = g.C + (long long)blockIdx.y * g.stride2C;
+    double* __restrict__ Ct = g.Ct ? g.Ct + (long long)blockIdx.y * g.stride2Ct : nullptr;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         const int row = m0 + wm * 32 + mi * 8 + gq;
@@ -234,9 +247,19 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static bool make_map(CUtensorMap* map, const double* base, long long ld, int rows, int K, int box_rows) {
+static bool make_map(CUtensorMap* map, const double* base, long long ld, int rows, int K, int box_rows,
+                     int batch2 = 1, long long stride2 = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
+    if (batch2 > 1) {
+        const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch2};
+        const cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)stride2 * 8};
+        const cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
     const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
@@ -251,7 +274,8 @@ static bool make_map(CUtensorMap* map, const double* base, long long ld, int row
 int launch_gemm_nt_tma(const GemmDesc& g, cudaStream_t stream) {
     static const bool disabled = getenv("GPMP_DEV_NO_TMA") != nullptr;
     if (disabled) return 1;
-    if (g.batch != 1 || g.batch2 != 1) return 1;
+    if (g.batch != 1) return 1;
+    if (g.batch2 > 1 && ((g.stride2A & 1) || (g.stride2B & 1) || g.stride2A <= 0 || g.stride2B <= 0)) return 1;
     if (g.A == g.C || g.B == g.C) return 1;  // in-place products keep the single-column-tile kernel
     if (g.K < TBK || (g.lda & 1) || (g.ldb & 1)) return 1;
     // Short k loops stay on the 64 x 64 kernel: with one 128 x 128 CTA per SM nothing covers a tile's prologue and
@@ -270,9 +294,11 @@ int launch_gemm_nt_tma(const GemmDesc& g, cudaStream_t stream) {
     } else {
         ntiles = (long long)a.tiles_m * a.tiles_n;
     }
-    if (ntiles < 148) return 1;  // cannot fill the machine with one 128 x 128 tile per SM: latency shapes
+    if (ntiles * g.batch2 < 148) return 1;  // cannot fill the machine with one 128 x 128 tile per SM: latency shapes
     CUtensorMap mapA, mapB;
-    if (!make_map(&mapA, g.A, g.lda, g.M, g.K, TBM) || !make_map(&mapB, g.B, g.ldb, g.N, g.K, TBN)) return 1;
+    if (!make_map(&mapA, g.A, g.lda, g.M, g.K, TBM, g.batch2, g.stride2A) ||
+        !make_map(&mapB, g.B, g.ldb, g.N, g.K, TBN, g.batch2, g.stride2B))
+        return 1;
     static unsigned long long configured = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -283,9 +309,9 @@ int launch_gemm_nt_tma(const GemmDesc& g, cudaStream_t stream) {
     }
     // algorithmic flops of the launch: triangular K ranges average to K/2 over a square operand
     const double kavg = g.krange == KR_FULL ? (double)g.K : 0.5 * (double)g.K;
-    const double work = 2.0 * (double)ntiles * TBM * TBN * kavg;
+    const double work = 2.0 * (double)ntiles * TBM * TBN * kavg * g.batch2;
     LaunchScope scope(KC_GEMM, work, stream);
-    gemm_nt_tma_kernel<<<(unsigned)ntiles, T_THREADS, T_SMEM, stream>>>(mapA, mapB, a);
+    gemm_nt_tma_kernel<<<dim3((unsigned)ntiles, (unsigned)g.batch2), T_THREADS, T_SMEM, stream>>>(mapA, mapB, a);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
 }
