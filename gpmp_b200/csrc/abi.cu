@@ -96,6 +96,24 @@ static LikWs lik_ws(int n, int q, int d) {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Which likelihood workspaces hold a leading block of T = L^-1 already (left by gpmp_lik_value under the tail of its
+// factorisation, potrf.cu early_inverse): workspace address -> size of the block.  Every call that rebuilds the fit
+// state of a workspace clears its entry first; gpmp_lik_grad / gpmp_lik_loo consume it.
+static std::mutex g_early_mutex;
+static std::vector<std::pair<const void*, int>> g_early;
+static void early_set(const void* work, int prefix) {
+    std::lock_guard<std::mutex> lock(g_early_mutex);
+    for (auto it = g_early.begin(); it != g_early.end(); ++it)
+        if (it->first == work) { g_early.erase(it); break; }
+    if (prefix > 0) g_early.emplace_back(work, prefix);
+}
+static int early_get(const void* work) {
+    std::lock_guard<std::mutex> lock(g_early_mutex);
+    for (auto& e : g_early)
+        if (e.first == work) return e.second;
+    return 0;
+}
+
 // Library-owned streams for the chunk pipeline of the batched criterion: one set per (device, caller stream).
 constexpr int BATCH_SLOTS = 4;
 struct BatchStreams {
@@ -352,6 +370,7 @@ static int lik_prepare(const gpmp_cov_spec* spec, const double* K_dev, long long
                        cudaStream_t s) {
     double* A = (double*)(base + w.off_A);
     int rc;
+    early_set(base, 0);  // the workspace's fit state is being rebuilt
     if (cudaMemsetAsync(info_dev, 0, sizeof(int), s) != cudaSuccess) return GPMP_ERR_CUDA;
     if (spec) rc = launch_matern_cov(spec, nullptr, 1, 0, x_dev, n, nullptr, n, A, w.lda, COV_SYM_LOWER, 0, s);
     else rc = launch_copy_lower(K_dev, ldk, A, w.lda, n, s);
@@ -401,10 +420,15 @@ int gpmp_lik_value(const gpmp_cov_spec* spec, const double* K_dev, long long ldk
     rc = lik_prepare(spec, K_dev, ldk, x_dev, n, z_dev, P_dev, q, w, base, info_dev, s);
     if (rc) return rc;
     char* pb = base + w.off_potrf;
+    // a workspace that also holds the buffers of the gradient: the leading block of T = L^-1 is computed under the
+    // tail of the factorisation (the K^-1 buffer is its scratch)
+    EarlyInverse early{(double*)(base + w.off_Tlo), (double*)(base + w.off_Tup), (double*)(base + w.off_Kinv), w.lda};
+    const bool with_t = work_bytes >= w.off_partial;
     rc = potrf_core((double*)(base + w.off_A), w.lda, 0, n, w.nrows, w.pw.NB, (double*)(pb + w.pw.off_tlo),
                     (double*)(pb + w.pw.off_tup), 0, (double*)(pb + w.pw.off_w), 0, info_dev, 0, 1, s,
-                    (double*)(pb + w.pw.off_tsub), 0, ceil_div(n, 128));
+                    (double*)(pb + w.pw.off_tsub), 0, ceil_div(n, 128), with_t ? &early : nullptr);
     if (rc) return rc;
+    if (with_t) early_set(base, early_prefix(n, w.pw.NB));
     return lik_finalize(n, q, w, base, out_dev, info_dev, s);
 }
 
@@ -485,7 +509,7 @@ int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, 
     double* Kinv = (double*)(base + w.off_Kinv);
     double* U = (double*)(base + w.off_U);
     int rc = potri_core(A, n, w.lda, w.pw.NB, (const double*)(pb + w.pw.off_tlo), (const double*)(pb + w.pw.off_tup),
-                        Tlo, Tup, Kinv, w.lda, s);
+                        Tlo, Tup, Kinv, w.lda, s, 1, 0, 0, 0, early_get(base));
     if (rc) return rc;
     URowsArgs u;
     u.R = A + (long long)n * w.lda; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;
@@ -610,7 +634,7 @@ int gpmp_lik_loo(int n, int q, void* work_dev, size_t work_bytes, const double* 
     double* Kinv = (double*)(base + w.off_Kinv);
     double* U = (double*)(base + w.off_U);
     int rc = potri_core(A, n, w.lda, w.pw.NB, (const double*)(pb + w.pw.off_tlo), (const double*)(pb + w.pw.off_tup),
-                        Tlo, Tup, Kinv, w.lda, s);
+                        Tlo, Tup, Kinv, w.lda, s, 1, 0, 0, 0, early_get(base));
     if (rc) return rc;
     URowsArgs u;
     u.R = A + (long long)n * w.lda; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;

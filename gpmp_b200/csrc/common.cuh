@@ -205,6 +205,8 @@ inline GemmDesc gemm_desc() {
     return g;
 }
 int launch_gemm_nt(const GemmDesc& g, cudaStream_t stream);
+// gemm.cu: the same product by persistent CTAs that keep off the SMs below sm_first (batch == 1 only)
+int launch_gemm_nt_persist(const GemmDesc& g, cudaStream_t stream, int sm_first);
 // gemm_tma.cu: 0 launched, 1 not a shape / environment it serves (take the cp.async kernel), < 0 error
 int launch_gemm_nt_tma(const GemmDesc& g, cudaStream_t stream);
 

@@ -75,16 +75,17 @@ struct GemmCfg {
     static constexpr int SMEM = STAGES * STAGE_BYTES;
 };
 
-template <int WM, int WN, int MI, int NI, int MINB, int STAGES, int SUBK>
-__global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKArgs a) {
+// One output tile: tile index t of the launch's tile list (already reversed if the launch asks for it), second /
+// first batch level yb / zb.  Every thread of the CTA calls it; shared memory may be reused by the next call after
+// a CTA-wide barrier.
+template <int WM, int WN, int MI, int NI, int STAGES, int SUBK>
+__device__ __forceinline__ void gemm_tile(const GemmKArgs& a, int t, long long yb, long long zb, unsigned char* smem) {
     using Cfg = GemmCfg<WM, WN, MI, NI, STAGES, SUBK>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS;
-    extern __shared__ __align__(1024) unsigned char smem[];
     const GemmDesc& g = a.g;
     int ti, tj;
-    decode_tile(a, g.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, ti, tj);
+    decode_tile(a, t, ti, tj);
     const int m0 = ti * BM, n0 = tj * BN;
-    const long long zb = blockIdx.z, yb = blockIdx.y;
     const double* __restrict__ A = g.A + zb * g.strideA + yb * g.stride2A;
     const double* __restrict__ B = g.B + zb * g.strideB + yb * g.stride2B;
     double* __restrict__ C = g.C + zb * g.strideC + yb * g.stride2C;
@@ -204,6 +205,64 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKA
     }
 }
 
+template <int WM, int WN, int MI, int NI, int MINB, int STAGES, int SUBK>
+__global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int t = a.g.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    gemm_tile<WM, WN, MI, NI, STAGES, SUBK>(a, t, blockIdx.y, blockIdx.z, smem);
+}
+
+// Persistent form for products that must leave part of the machine to other work (the triangular-inverse levels
+// that run under the tail of a factorisation, potrf.cu): CTAs that find themselves on an SM below `sm_first` exit at
+// once; the others draw (tile, pair) indices from a counter in global memory until the list is exhausted.  The last
+// CTA to leave resets the counter pair for its next user.
+__device__ unsigned int g_gemm_counters[2 * 1024];
+template <int WM, int WN, int MI, int NI, int MINB, int STAGES, int SUBK>
+__global__ void __launch_bounds__(WM* WN * 32, MINB)
+gemm_nt_persist_kernel(const GemmKArgs a, int ntiles, int slot, int sm_first) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ unsigned int next;
+    unsigned int* ctr = g_gemm_counters + 2 * slot;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned int total = (unsigned int)ntiles * (unsigned int)a.g.batch2;
+    if ((int)smid >= sm_first) {
+        for (;;) {
+            __syncthreads();  // the previous tile's shared memory and `next` are no longer read
+            if (threadIdx.x == 0) next = atomicAdd(&ctr[0], 1u);
+            __syncthreads();
+            const unsigned int w = next;
+            if (w >= total) break;
+            const int yb = (int)(w / (unsigned int)ntiles), t0 = (int)(w - (unsigned int)yb * (unsigned int)ntiles);
+            gemm_tile<WM, WN, MI, NI, STAGES, SUBK>(a, a.g.reverse ? ntiles - 1 - t0 : t0, yb, 0, smem);
+        }
+    }
+    // Leaving.  The last CTA to leave finishes whatever is left of the list itself, wherever it runs (only if every
+    // other CTA was turned away from its SM -- correctness must not depend on where the scheduler places CTAs),
+    // and resets the counter pair.
+    __shared__ unsigned int last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&ctr[1], 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!last) return;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next = atomicAdd(&ctr[0], 1u);
+        __syncthreads();
+        const unsigned int w = next;
+        if (w >= total) break;
+        const int yb = (int)(w / (unsigned int)ntiles), t0 = (int)(w - (unsigned int)yb * (unsigned int)ntiles);
+        gemm_tile<WM, WN, MI, NI, STAGES, SUBK>(a, a.g.reverse ? ntiles - 1 - t0 : t0, yb, 0, smem);
+    }
+    if (threadIdx.x == 0) {
+        ctr[0] = 0u;
+        ctr[1] = 0u;
+        __threadfence();
+    }
+}
+
 template <int WM, int WN, int MI, int NI, int MINB, int STAGES = 3, int SUBK = 2>
 static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     using Cfg = GemmCfg<WM, WN, MI, NI, STAGES, SUBK>;
@@ -232,6 +291,48 @@ static int launch_cfg(const GemmDesc& g, cudaStream_t stream) {
     LaunchScope scope(KC_GEMM, work, stream);
     dim3 grid((unsigned)ntiles, (unsigned)g.batch2, (unsigned)g.batch);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(a);
+    GPMP_CHECK_LAUNCH();
+    return GPMP_OK;
+}
+
+int launch_gemm_nt_persist(const GemmDesc& g, cudaStream_t stream, int sm_first) {
+    if (g.M <= 0 || g.N <= 0 || g.batch2 <= 0) return GPMP_OK;
+    if (g.batch != 1) return GPMP_ERR_ARG;
+    if ((g.lda & 1) || (g.ldb & 1) || (g.ldc & 1) || (g.stride2A & 1) || (g.stride2B & 1) || (g.stride2C & 1))
+        return GPMP_ERR_ALIGN;
+    using Cfg = GemmCfg<2, 2, 4, 4, 3, 1>;
+    auto kern = gemm_nt_persist_kernel<2, 2, 4, 4, 4, 3, 1>;
+    static unsigned long long configured = 0;
+    static unsigned int next_slot = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+            return GPMP_ERR_CUDA;
+        configured |= 1ull << (dev & 63);
+    }
+    GemmKArgs a;
+    a.g = g;
+    a.tiles_m = ceil_div(g.M, Cfg::BM);
+    a.tiles_n = ceil_div(g.N, Cfg::BN);
+    long long ntiles;
+    if (g.lower) {
+        if (a.tiles_n > a.tiles_m) a.tiles_n = a.tiles_m;
+        ntiles = (long long)a.tiles_n * (a.tiles_n + 1) / 2 + (long long)(a.tiles_m - a.tiles_n) * a.tiles_n;
+    } else {
+        ntiles = (long long)a.tiles_m * a.tiles_n;
+    }
+    const long long total = ntiles * g.batch2;
+    const double kavg = g.krange == KR_FROM_ROW || g.krange == KR_TO_ROW || g.krange == KR_FROM_COL ||
+                                g.krange == KR_TO_COL
+                            ? 0.5 * (double)g.K
+                            : (double)g.K;
+    LaunchScope scope(KC_GEMM, 2.0 * (double)total * Cfg::BM * Cfg::BN * kavg, stream);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned int grid = (unsigned int)(total < 4LL * sms ? total : 4LL * sms);
+    const int slot = (int)(next_slot++ & 1023u);  // (a slot is reused 1024 persistent launches later)
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(a, (int)ntiles, slot, sm_first);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
 }

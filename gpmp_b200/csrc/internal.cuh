@@ -38,14 +38,20 @@ int launch_maternp_elementwise(int p, const double* h, double* k, double* dk, lo
 
 // ---- potrf.cu
 int potrf_block_size(int n);
+// Buffers of T = L^-1 (Tlo lower, Tup = T^T upper, both n x ld) and an n x ld scratch: when given, the factorisation
+// also leaves the leading early_prefix(n, NB) x early_prefix(n, NB) block of T complete (computed under its tail).
+struct EarlyInverse { double* Tlo; double* Tup; double* X; long long ld; };
+int early_prefix(int n, int NB);
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream, double* Tsub = nullptr, long long strideTsub = 0, int tsub_tiles = 0);
+               cudaStream_t stream, double* Tsub = nullptr, long long strideTsub = 0, int tsub_tiles = 0,
+               const EarlyInverse* early = nullptr);
 // Tsub: block-diagonal (32x32) tile inverses for the substitution solve; tsub_tiles = 128x128 tiles it holds per
 // matrix (ceil(n / 128) for the look-ahead path of a single matrix, 1 for the batched value-only path)
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
                double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream, int batch = 1,
-               long long strideL = 0, long long strideTc = 0, long long strideT = 0);
+               long long strideL = 0, long long strideTc = 0, long long strideT = 0, int prefix = 0);
+// prefix: the leading prefix x prefix block of T is already complete (EarlyInverse)
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,
                    double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream,
                    int first_block = 0);

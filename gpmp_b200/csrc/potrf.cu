@@ -1566,15 +1566,20 @@ int potrf_block_size(int n) {
 // Doubling pass over the diagonal blocks of size s inside [0, len): for each pair (first block full,
 // second block of size s2 <= s) computes T21 = -T22 * L21 * T11 into Tlo (and its mirror into Tup).
 // L, Tlo, Tup, Xt are addressed from the origin of the range; Xt is scratch with the same indexing.
+// pair0: the first pair0 full pairs are already done (the leading block inverted under the factorisation's tail);
+// sm_first >= 0: persistent launches that keep off the SMs below sm_first (batch == 1 only).
 static int doubling_level(const double* L, long long ldl, long long strideL, double* Tlo, double* Tup,
                           long long ldt, long long strideT, double* Xt, long long ldx, long long strideX,
-                          int len, int s, int batch, cudaStream_t stream) {
+                          int len, int s, int batch, cudaStream_t stream, int pair0 = 0, int sm_first = -1) {
     const int npairs_full = len / (2 * s);
     const int rem = len - npairs_full * 2 * s;  // leftover: a ragged pair if rem > s
+    auto launch = [&](const GemmDesc& d) {
+        return sm_first >= 0 && batch == 1 ? launch_gemm_nt_persist(d, stream, sm_first) : launch_gemm_nt(d, stream);
+    };
     for (int pass = 0; pass < 2; ++pass) {
         int np, s2;
         long long o;  // origin (block index offset) of the first pair of this pass
-        if (pass == 0) { np = npairs_full; s2 = s; o = 0; }
+        if (pass == 0) { np = npairs_full - min(pair0, npairs_full); s2 = s; o = (long long)min(pair0, npairs_full) * 2 * s; }
         else { np = rem > s ? 1 : 0; s2 = rem - s; o = (long long)npairs_full * 2 * s; }
         if (np <= 0) continue;
         // Xt (s x s2) = Tup11 (rows j, k >= j) x L21^T   [NT: A = Tup11, B = L21]
@@ -1583,7 +1588,7 @@ static int doubling_level(const double* L, long long ldl, long long strideL, dou
         g.B = L + (o + s) * ldl + o; g.ldb = ldl; g.strideB = strideL; g.stride2B = 2LL * s * (ldl + 1);
         g.C = Xt + o * ldx + (o + s); g.ldc = ldx; g.strideC = strideX; g.stride2C = 2LL * s * (ldx + 1);
         g.M = s; g.N = s2; g.K = s; g.krange = KR_FROM_ROW; g.batch = batch; g.batch2 = np;
-        int rc = launch_gemm_nt(g, stream);
+        int rc = launch(g);
         if (rc) return rc;
         // T21 (s2 x s) = -Tlo22 (rows i, k <= i) x Xt^T  [NT: A = Tlo22, B = Xt]
         GemmDesc h = gemm_desc();
@@ -1593,7 +1598,7 @@ static int doubling_level(const double* L, long long ldl, long long strideL, dou
         h.Ct = Tup + o * ldt + (o + s); h.ldct = ldt; h.strideCt = strideT; h.stride2Ct = 2LL * s * (ldt + 1);
         h.M = s2; h.N = s; h.K = s2; h.alpha = -1.0; h.krange = KR_TO_ROW; h.reverse = 1;
         h.batch = batch; h.batch2 = np;
-        rc = launch_gemm_nt(h, stream);
+        rc = launch(h);
         if (rc) return rc;
     }
     return GPMP_OK;
@@ -1738,17 +1743,23 @@ static int group_panel(const PotrfCtx& c, int k0, double* Wg, long long strideW,
 
 // NB-wide inverses of the diagonal blocks from the 128-tile inverses, by doubling; all full blocks of one
 // matrix go in one batched launch per level.  Xscr: scratch of >= nblk * NB * NB doubles per batch entry.
-static int block_inverses(const PotrfCtx& c, double* Xscr, long long strideX, cudaStream_t stream) {
+// g0 / g1 (single matrices only): restrict to the full groups [g0, g1) (g1 < 0: to the end, ragged last group
+// included).
+static int block_inverses(const PotrfCtx& c, double* Xscr, long long strideX, cudaStream_t stream, int g0 = 0,
+                          int g1 = -1) {
     const int NB = c.NB, n = c.n;
     if (NB <= PT) return GPMP_OK;
     if (c.batch > 1 && c.Tsub != nullptr) return GPMP_OK;  // value-only batched path: no tile inverses exist
-    const int nfull = n / NB, rem = n - nfull * NB;
+    const int nfull = n / NB, rem = g1 >= 0 ? 0 : n - nfull * NB;
+    const int gl = g1 >= 0 ? min(g1, nfull) : nfull;
     int rc;
     for (int s = PT; s < NB; s *= 2) {
         if (c.batch == 1) {
-            if (nfull > 0) {
-                rc = doubling_level(c.A, c.lda, (long long)NB * (c.lda + 1), c.Tlo, c.Tup, NB, (long long)NB * NB,
-                                    Xscr, NB, (long long)NB * NB, NB, s, nfull, stream);
+            if (gl > g0) {
+                rc = doubling_level(c.A + (long long)g0 * NB * (c.lda + 1), c.lda, (long long)NB * (c.lda + 1),
+                                    c.Tlo + (long long)g0 * NB * NB, c.Tup + (long long)g0 * NB * NB, NB,
+                                    (long long)NB * NB, Xscr + (long long)g0 * NB * NB, NB, (long long)NB * NB, NB, s,
+                                    gl - g0, stream);
                 if (rc) return rc;
             }
         } else {
@@ -1800,6 +1811,7 @@ struct LookAhead {
     cudaStream_t side = nullptr;    // the chain: what the next tile factorisation is waiting for
     cudaStream_t helper = nullptr;  // updates inside the next column group that are not on the chain
     cudaStream_t ahead[LA_DEPTH] = {};  // look-ahead updates: group g receives panels g-D .. g-2 on ahead[g % D]
+    cudaStream_t early = nullptr;   // the leading block of T = L^-1, inverted under the factorisation's tail
     std::vector<cudaEvent_t> ev;
     bool ok = false;
 };
@@ -1825,6 +1837,7 @@ static LookAhead* lookahead(cudaStream_t caller, int nevents) {
                      cudaStreamCreateWithPriority(&la->helper, cudaStreamNonBlocking, hi) == cudaSuccess;
             for (int i = 0; i < LA_DEPTH && la->ok; ++i)
                 la->ok = cudaStreamCreateWithPriority(&la->ahead[i], cudaStreamNonBlocking, mid) == cudaSuccess;
+            la->ok = la->ok && cudaStreamCreateWithPriority(&la->early, cudaStreamNonBlocking, lo) == cudaSuccess;
             g_la_sets.push_back(la);
         }
     }
@@ -1835,6 +1848,69 @@ static LookAhead* lookahead(cudaStream_t caller, int nevents) {
         la->ev.push_back(e);
     }
     return la;
+}
+
+struct CopyDiagArgs {
+    const double* slo; const double* sup; int NB;  // compact blocks (ld NB)
+    double* dlo; double* dup; long long ld;        // full matrices
+    int n;
+    long long strideS, strideD;                    // batch strides (blockIdx.z) of the compact / full matrices
+};
+__global__ void copy_diag_blocks_kernel(const CopyDiagArgs a) {
+    const int b = blockIdx.y;
+    const int nbk = min(a.NB, a.n - b * a.NB);
+    const long long src0 = (long long)blockIdx.z * a.strideS + (long long)b * a.NB * a.NB;
+    const long long dst0 = (long long)blockIdx.z * a.strideD + (long long)b * a.NB * (a.ld + 1);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)nbk * nbk;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / nbk), c = (int)(e - (long long)r * nbk);
+        a.dlo[dst0 + (long long)r * a.ld + c] = a.slo[src0 + (long long)r * a.NB + c];
+        a.dup[dst0 + (long long)r * a.ld + c] = a.sup[src0 + (long long)r * a.NB + c];
+    }
+}
+
+// ---- the leading block of T = L^-1 under the tail of the factorisation ---------------------------------------
+// At n = 8192 the last third of the factorisation is bound by the chain's latency and leaves most SMs idle, while
+// the gradient that follows starts with n^3/3 of GEMM work (T = L^-1 by block doubling) whose levels inside the
+// leading P x P block only need the first P columns of L -- final long before the factorisation ends.  When the
+// caller hands over the buffers of T (gpmp_lik_value with a gradient-sized workspace) those levels are enqueued on a
+// low-priority stream once the bulk updates have run dry, as persistent GEMMs that keep off the first EARLY_SM_FIRST
+// SMs (where the chain's whole-SM CTAs then always find room).  early_prefix() is the contract between the two
+// calls: a pure function of (n, NB), so that gpmp_lik_grad knows which pairs are done without any state.
+constexpr int EARLY_SM_FIRST = 40;
+static int early_sm_first() {
+    static const int v = dev_env("GPMP_DEV_EARLYSM");
+    return v > 0 ? v : EARLY_SM_FIRST;
+}
+int early_prefix(int n, int NB) {
+    static const bool off = dev_env("GPMP_DEV_NOEARLY") != 0;
+    if (off || NB < 256 || n % NB != 0) return 0;
+    const int nblk = n / NB;
+    if (nblk < 8 || n > 16384) return 0;  // (beyond that the bulk updates bound the whole factorisation)
+    int p = 1;
+    while (2 * p <= nblk / 2) p *= 2;
+    return p * NB;
+}
+
+static int early_inverse(const PotrfCtx& c, const EarlyInverse& e, int P, cudaStream_t stream, int sm_first) {
+    const int NB = c.NB;
+    // NB-wide inverses of the first P / NB diagonal blocks from their tile inverses (scratch: the K^-1 buffer)
+    int rc = block_inverses(c, e.X, 0, stream, 0, P / NB);
+    if (rc) return rc;
+    {
+        CopyDiagArgs cd;
+        cd.slo = c.Tlo; cd.sup = c.Tup; cd.NB = NB; cd.dlo = e.Tlo; cd.dup = e.Tup; cd.ld = e.ld; cd.n = c.n;
+        cd.strideS = 0; cd.strideD = 0;
+        LaunchScope scope(KC_SMALL, 0.0, stream);
+        dim3 grid(min(64, ceil_div(NB * NB, 256)), P / NB, 1);
+        copy_diag_blocks_kernel<<<grid, 256, 0, stream>>>(cd);
+        GPMP_CHECK_LAUNCH();
+    }
+    for (long long s = NB; s < P; s *= 2) {
+        rc = doubling_level(c.A, c.lda, 0, e.Tlo, e.Tup, e.ld, 0, e.X, e.ld, 0, P, (int)s, 1, stream, 0, sm_first);
+        if (rc) return rc;
+    }
+    return GPMP_OK;
 }
 
 // Core factorisation.
@@ -1850,7 +1926,7 @@ static LookAhead* lookahead(cudaStream_t caller, int nevents) {
 // a panel buffer.
 int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, int NB, double* Tlo, double* Tup,
                long long strideT, double* W, long long strideW, int* info, long long strideInfo, int batch,
-               cudaStream_t stream, double* Tsub, long long strideTsub, int tsub_tiles) {
+               cudaStream_t stream, double* Tsub, long long strideTsub, int tsub_tiles, const EarlyInverse* early) {
     if (n <= 0) return GPMP_OK;
     // batched value-only runs: the few whitening rows below the matrix travel as the solve kernel's extra strip
     const int nextra = (batch > 1 && Tsub != nullptr && nrows > n && nrows - n <= TS_EXTRA) ? nrows - n : 0;
@@ -1875,7 +1951,11 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
             rc = trailing_update(c, k, Wb[0] + (long long)gw * NB, NB, strideW, 0, -1, stream);
             if (rc) return rc;
         }
-        return block_inverses(c, Wb[0], strideW, stream);
+        rc = block_inverses(c, Wb[0], strideW, stream);
+        if (rc) return rc;
+        // the contract of early_prefix() holds on this path too (in stream order, nothing to overlap with)
+        const int P0 = early && batch == 1 ? early_prefix(n, NB) : 0;
+        return P0 > 0 ? early_inverse(c, *early, P0, stream, -1) : GPMP_OK;
     }
     // Streams.  s (caller's): the bulk K=NB updates.  B (chain): only what the next tile factorisation waits
     // for -- the update of the next 128 columns, the tile kernel, the solve below it.  H (helper): the other
@@ -1955,6 +2035,12 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
         cudaEventRecord(ev(g, E_PANEL), B);
         return GPMP_OK;
     };
+    const int P_early = early ? early_prefix(n, NB) : 0;
+    static const int forced_b = dev_env("GPMP_DEV_EARLYB");
+    // (as soon as the leading block's columns are final: measured at n = 8192, evals/s with the trigger after group
+    // 7 / 8 / 9 / 10 / 11 / 12: 50.4 / 50.3 / 50.2 / 49.9 / 49.6 / 48.9; without the early block 48.6)
+    const int b_early = forced_b > 0 ? forced_b : P_early / NB - 1;
+    bool early_started = false;
     // fork
     if (cudaEventRecord(la->ev[0], s) != cudaSuccess || cudaStreamWaitEvent(B, la->ev[0], 0) != cudaSuccess ||
         cudaStreamWaitEvent(H, la->ev[0], 0) != cudaSuccess)
@@ -2005,6 +2091,17 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
         rc = trailing_update(c, k, Pk, lda, 0, min(Nn, D * NB), -1, s);
         if (rc) return rc;
         cudaEventRecord(ev(b, E_REST), s);
+        if (P_early > 0 && !early_started && b >= b_early) {
+            // the bulk updates have (nearly) run dry and the first P_early columns of L are final: the levels of
+            // T = L^-1 inside the leading block, behind the tile inverses the helper stream has been given so far
+            cudaStream_t E = serial ? stream : la->early;
+            cudaEventRecord(la->ev[4 + LA_DEPTH], H);
+            cudaStreamWaitEvent(E, la->ev[4 + LA_DEPTH], 0);
+            cudaStreamWaitEvent(E, ev(b, E_REST), 0);
+            rc = early_inverse(c, *early, P_early, E, early_sm_first());
+            if (rc) return rc;
+            early_started = true;
+        }
         // next group's steps
         if (nb_next > 0) {
             rc = run_group(b + 1, r0, Wb[(b + 1) & 1], nb_next > head0);
@@ -2020,7 +2117,16 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
         if (cudaEventRecord(la->ev[4 + i], Q[i]) != cudaSuccess ||
             cudaStreamWaitEvent(s, la->ev[4 + i], 0) != cudaSuccess)
             return GPMP_ERR_CUDA;
-    return block_inverses(c, Wb[0], strideW, s);
+    if (P_early > 0) {
+        if (!early_started) {
+            rc = early_inverse(c, *early, P_early, s, -1);
+            if (rc) return rc;
+        } else if (!serial) {
+            if (cudaEventRecord(la->ev[3], la->early) != cudaSuccess || cudaStreamWaitEvent(s, la->ev[3], 0) != cudaSuccess)
+                return GPMP_ERR_CUDA;
+        }
+    }
+    return block_inverses(c, Wb[0], strideW, s, P_early / NB, -1);
 }
 
 // ---- panel-partitioned factorisation across GPUs ------------------------------------------------------
@@ -2121,28 +2227,9 @@ int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo,
 }
 
 // ---- potri: Tlo/Tup (n x n) from L and the compact NB-block inverses, then Kinv = T^T T (lower) ----
-struct CopyDiagArgs {
-    const double* slo; const double* sup; int NB;  // compact blocks (ld NB)
-    double* dlo; double* dup; long long ld;        // full matrices
-    int n;
-    long long strideS, strideD;                    // batch strides (blockIdx.z) of the compact / full matrices
-};
-__global__ void copy_diag_blocks_kernel(const CopyDiagArgs a) {
-    const int b = blockIdx.y;
-    const int nbk = min(a.NB, a.n - b * a.NB);
-    const long long src0 = (long long)blockIdx.z * a.strideS + (long long)b * a.NB * a.NB;
-    const long long dst0 = (long long)blockIdx.z * a.strideD + (long long)b * a.NB * (a.ld + 1);
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)nbk * nbk;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(e / nbk), c = (int)(e - (long long)r * nbk);
-        a.dlo[dst0 + (long long)r * a.ld + c] = a.slo[src0 + (long long)r * a.NB + c];
-        a.dup[dst0 + (long long)r * a.ld + c] = a.sup[src0 + (long long)r * a.NB + c];
-    }
-}
-
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
                double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream, int batch,
-               long long strideL, long long strideTc, long long strideT) {
+               long long strideL, long long strideTc, long long strideT, int prefix) {
     // batched form: entry b reads L + b strideL and the compact inverses + b strideTc, and writes Tlo / Tup / Kinv
     // + b strideT (all three share one stride)
     if (n <= 0 || batch <= 0) return GPMP_OK;
@@ -2158,8 +2245,11 @@ int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_
         GPMP_CHECK_LAUNCH();
     }
     // doubling NB -> n; scratch for X^T: the Kinv buffer (written only by the final product)
+    // (prefix: the leading prefix x prefix block of T was completed under the tail of the factorisation)
     for (long long s = NB; s < n; s *= 2) {
-        rc = doubling_level(L, ldl, strideL, Tlo, Tup, ldk, strideT, Kinv, ldk, strideT, n, (int)s, batch, stream);
+        const int pair0 = (batch == 1 && s < prefix) ? (int)(prefix / (2 * s)) : 0;
+        rc = doubling_level(L, ldl, strideL, Tlo, Tup, ldk, strideT, Kinv, ldk, strideT, n, (int)s, batch, stream,
+                            pair0);
         if (rc) return rc;
     }
     // Kinv (lower) = T^T T :  Kinv_ij = sum_{k >= i} Tup[i][k] Tup[j][k]

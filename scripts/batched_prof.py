@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); crit.values_device(thd); e1.record(); torch.cuda.synchronize()
 out = {"sweep_ms": e0.elapsed_time(e1)}
-_abi.prof_enable(True)
+_abi.prof_enable(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 crit.values_device(thd)
 torch.cuda.synchronize()
 for c, nm in enumerate(["matern", "gemm", "potf2", "contract", "small", "batched"]):

@@ -26,7 +26,9 @@ if want_grad:
     _abi.prof_enable(False); [_abi.prof_read(c) for c in range(6)]; _abi.prof_enable(True)
     ops.lik_grad(st, False, False)
 else:
-    ops.lik_value(spec, None, xd, zd, P, False)
+    # "withgrad": the forward pass as the value+gradient path runs it (gradient-sized workspace: the leading block
+    # of T = L^-1 is computed under the tail of the factorisation)
+    ops.lik_value(spec, None, xd, zd, P, len(sys.argv) > 4 and sys.argv[4] == "withgrad")
 torch.cuda.synchronize()
 lib = _abi.lib()
 buf = (C.c_double * (4 * 4000))()
