@@ -732,3 +732,32 @@ def test_headline_size_properties(gp):
     fm = m.negative_log_restricted_likelihood(th0 - h * dirn, xd, zd).item()
     fd = (fp - fm) / (2 * h)
     assert abs(fd - float(g.numpy() @ dirn)) <= 1e-5 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("n", [4096, 16384])
+def test_early_inverse_sizes_properties(gp, n):
+    """Sizes at which the leading block of T = L^-1 is computed under the tail of the factorisation (potrf.cu
+    early_inverse: n a multiple of the group width with at least 8 groups, up to 16384): the gradient that consumes
+    that block must satisfy the closed form d value / d log sigma2 = 0.5 ((n-q) - quad) and a central finite
+    difference of the value (which runs WITHOUT the early block: value-sized workspace) along a random direction."""
+    x, z, th0 = cases.headline(n=n)
+    m = _model(gp, "const", 2, False, th0)
+    xd, zd = gp.num.asarray(x), gp.num.asarray(z)
+    tp = torch.tensor(th0, requires_grad=True)
+    v = m.negative_log_restricted_likelihood(tp, xd, zd)
+    (g,) = torch.autograd.grad(v, tp)
+    quad = m.norm_k_sqrd(xd, zd, th0).item()
+    closed = 0.5 * ((n - 1) - quad)
+    err = abs(g[0].item() - closed) / max(1.0, abs(closed))
+    print(f"[parity] n={n}: d/dlog sigma2 {g[0].item():.12g} vs closed form {closed:.12g} (rel {err:.2e})")
+    assert err <= 1e-8
+    rng = np.random.default_rng(3)
+    dirn = rng.standard_normal(th0.shape)
+    dirn /= np.linalg.norm(dirn)
+    h = 1e-4
+    fp = m.negative_log_restricted_likelihood(th0 + h * dirn, xd, zd).item()
+    fm = m.negative_log_restricted_likelihood(th0 - h * dirn, xd, zd).item()
+    fd = (fp - fm) / (2 * h)
+    assert abs(fd - float(g.numpy() @ dirn)) <= 1e-5 * max(1.0, abs(fd))
+    # the value computed with and without the gradient-sized workspace is the same number
+    assert abs(v.item() - m.negative_log_restricted_likelihood(th0, xd, zd).item()) <= 1e-12 * abs(v.item())
