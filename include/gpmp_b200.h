@@ -17,8 +17,11 @@
  *    device `info` word, LAPACK style; the host wrapper maps it to torch.linalg.LinAlgError / +inf
  *    (reference convention: gpmp/core/likelihood.py:45-48,121-124).
  *  - Return value: 0 = enqueued; negative = rejected (GPMP_ERR_*).
- *  - Re-entrant per (stream, workspace); not internally locked (all reference callers are
- *    single-threaded loops: kernel/parameter_selection.py:253, mcmc/param_posterior.py:752).
+ *  - Re-entrant per (stream, workspace): the library-owned look-ahead streams / events exist once per
+ *    (device, caller stream), and the only host-side state shared between calls -- their registry and the
+ *    record of which likelihood workspaces already hold a leading block of T = L^-1 (see gpmp_lik_value) --
+ *    is mutex-protected.  (All reference callers are single-threaded loops:
+ *    kernel/parameter_selection.py:253, mcmc/param_posterior.py:752.)
  */
 #ifndef GPMP_B200_H
 #define GPMP_B200_H
@@ -159,6 +162,11 @@ int gpmp_transpose(const double* in_dev, long long ldi, double* out_dev, long lo
  *   (out_dev holds 8 doubles)
  *   spec != NULL: K is built from (spec, x_dev) by the fused Matern kernel (lower triangle only);
  *   spec == NULL: K_dev (n x n, lower triangle read) is a user-composed covariance.
+ *   With a workspace sized for the gradient (want_grad = 1) and n a multiple of the column-group width with
+ *   8..32 groups, the call also computes the leading block of T = L^-1 (the first half of the columns,
+ *   rounded down to a power of two of groups) under the latency-bound tail of the factorisation, on a
+ *   low-priority library stream joined before the call's last kernel; gpmp_lik_grad / gpmp_lik_loo on the same
+ *   workspace skip that block.  Values are unaffected.
  * gpmp_lik_grad (after gpmp_lik_value on the same workspace, which must have been sized with
  * want_grad = 1):
  *   grad_dev[0 .. 1+noise+d)  = d value / d covparam            (spec != NULL)
