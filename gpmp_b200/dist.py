@@ -116,3 +116,55 @@ def predict_distributed(model, xi, zi, xt, group=None, convert_out=True, fitted=
     if convert_out:
         return num.to_np(mean), num.to_np(var)
     return mean, var
+
+
+class DrivenSweeps:
+    """One rank drives, the others serve: for samplers whose host control flow cannot run in lock step on every
+    rank (GPmp's SMC / MH draw from unseeded generators, gpmp/mcmc/smc.py:129,535), rank 0 runs the sampler and
+    calls `sweeps(rows)` for every particle set; the other ranks sit in `sweeps.serve()`.  Before each sweep rank 0
+    broadcasts the row count and the rows, then EVERY rank calls `fn(rows)` -- a collective function that evaluates
+    its own block of rows and all-gathers the results (BatchedCriterion with a process group) -- so the particle
+    loop of mcmc/param_posterior.py:752 is sharded although only one rank holds the sampler's state.
+
+        sweeps = DrivenSweeps(crit, dim, group)       # crit: BatchedCriterion(..., group=group)
+        if rank != 0: sweeps.serve()                  # returns when rank 0 calls sweeps.stop()
+        else: ...sampler calling sweeps(thetas)...; sweeps.stop()
+    """
+
+    def __init__(self, fn, dim, group=None, device=None):
+        self.fn, self.dim, self.group = fn, int(dim), group
+        self.rank, self.size = world(group)
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        self.src = td.get_global_rank(group, 0) if (group is not None and self.size > 1) else 0
+
+    def __call__(self, rows):
+        import numpy as np
+
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.dim)
+        if self.size > 1:
+            if self.rank != 0:
+                raise RuntimeError("DrivenSweeps: only rank 0 drives; the other ranks call serve()")
+            td.broadcast(torch.tensor([rows.shape[0]], dtype=torch.int64, device=self.device), src=self.src,
+                         group=self.group)
+            td.broadcast(torch.as_tensor(rows, device=self.device), src=self.src, group=self.group)
+        return self.fn(rows)
+
+    def serve(self):
+        """Ranks != 0: evaluate sweeps until rank 0 sends the stop word; returns the number of sweeps served."""
+        served = 0
+        while self.size > 1:
+            hdr = torch.zeros(1, dtype=torch.int64, device=self.device)
+            td.broadcast(hdr, src=self.src, group=self.group)
+            cnt = int(hdr.item())
+            if cnt < 0:
+                break
+            buf = torch.empty((cnt, self.dim), dtype=torch.float64, device=self.device)
+            td.broadcast(buf, src=self.src, group=self.group)
+            self.fn(buf.cpu().numpy())
+            served += 1
+        return served
+
+    def stop(self):
+        if self.size > 1 and self.rank == 0:
+            td.broadcast(torch.tensor([-1], dtype=torch.int64, device=self.device), src=self.src, group=self.group)

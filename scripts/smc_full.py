@@ -7,7 +7,7 @@ with its particle loop (mcmc/param_posterior.py:752) bound to the batched sweep 
 
 The sampler itself (host control flow, unseeded generators: smc.py:129,535) runs on rank 0 only; before every sweep
 rank 0 broadcasts the particle set, every rank evaluates its block of rows and the values are all-gathered
-(BatchedCriterion with a process group).  The other ranks sit in a serve loop until rank 0 sends the stop word.
+(gpmp_b200.dist.DrivenSweeps around a BatchedCriterion with a process group).
 Rank 0 prints one JSON line: wall time, sweeps, sweeps/s, particle evaluations/s, posterior mean / std of theta.
 """
 import json
@@ -48,31 +48,15 @@ model = gp.core.Model(lambda x_, param: gnp.ones((x_.shape[0], 1)),
                       lambda a, b, cp, pairwise=False: gp.kernel.maternp_covariance(a, b, 2, cp, pairwise),
                       None, None)
 crit = b200.BatchableCriterion(model, x, z, 2, kind="reml", group=(dist.group.WORLD if world > 1 else None))
-dim = d + 1
 if world > 1:
-    inner = crit.crit  # the sharded BatchedCriterion: every rank must call it with the same thetas
+    from gpmp_b200.dist import DrivenSweeps
 
-    def served(th):
-        th = np.ascontiguousarray(th, dtype=np.float64)
-        hdr = torch.tensor([th.shape[0]], dtype=torch.int64, device="cuda")
-        dist.broadcast(hdr, src=0)
-        buf = torch.as_tensor(th, device="cuda")
-        dist.broadcast(buf, src=0)
-        return inner(th)
-
+    sweeps = DrivenSweeps(crit.crit, d + 1, dist.group.WORLD)  # crit.crit: the sharded BatchedCriterion
     if rank != 0:
-        while True:
-            hdr = torch.zeros(1, dtype=torch.int64, device="cuda")
-            dist.broadcast(hdr, src=0)
-            cnt = int(hdr.item())
-            if cnt < 0:
-                break
-            buf = torch.empty((cnt, dim), dtype=torch.float64, device="cuda")
-            dist.broadcast(buf, src=0)
-            inner(buf.cpu().numpy())
+        sweeps.serve()
         dist.destroy_process_group()
         sys.exit(0)
-    crit.crit = served
+    crit.crit = sweeps
 crit.batched(np.tile(th0, (N, 1)))  # warm-up: workspace, streams
 crit.sweeps = crit.evaluations = 0
 torch.cuda.synchronize()
@@ -100,5 +84,5 @@ if rank == 0:
         "theta_data_generating": th0.tolist()}))
 b200.uninstall()
 if world > 1:
-    dist.broadcast(torch.tensor([-1], dtype=torch.int64, device="cuda"), src=0)
+    sweeps.stop()
     dist.destroy_process_group()

@@ -60,6 +60,45 @@ def test_particle_sharding_world2_gloo(N):
     assert sorted((lo, hi) for _, lo, hi, _ in res) == [gdist.block_bounds(N, 0, 2), gdist.block_bounds(N, 1, 2)]
 
 
+def _driven_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def sharded(rows):  # what BatchedCriterion.__call__ does, with a CPU stand-in for the device sweep
+        N = rows.shape[0]
+        lo, hi = gdist.shard_bounds(N)
+        local = torch.as_tensor((rows[lo:hi] ** 2).sum(axis=1) + 100.0 * rank * 0.0)
+        return gdist.all_gather_rows(local, N).numpy()
+
+    sweeps = gdist.DrivenSweeps(sharded, dim=3, device="cpu")
+    if rank != 0:
+        q.put(("served", sweeps.serve()))
+    else:
+        rng = np.random.default_rng(os.getpid())  # only rank 0 draws: the ranks need not be in lock step
+        ok = True
+        for N in (7, 1, 12, 5):  # the particle count changes from sweep to sweep (rows outside the box are dropped)
+            rows = rng.standard_normal((N, 3))
+            ok = ok and np.allclose(sweeps(rows), (rows ** 2).sum(axis=1), rtol=0, atol=1e-15)
+        sweeps.stop()
+        q.put(("driver", ok))
+    dist.destroy_process_group()
+
+
+def test_driven_sweeps_world2_gloo():
+    """The multi-rank form of the SMC / MH particle sweep: rank 0 runs the sampler, rank 1 serves."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_driven_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res["driver"] is True and res["served"] == 4
+
+
 def test_bench_inputs_are_the_seeded_headline_case():
     sys.path.insert(0, ROOT)
     import bench
