@@ -350,6 +350,23 @@ int gpmp_transpose(const double* in_dev, long long ldi, double* out_dev, long lo
     return launch_transpose(in_dev, ldi, out_dev, ldo, rows, cols, (cudaStream_t)stream);
 }
 
+// development / test hook (not declared in the header): the persistent form of gpmp_gemm_nt (gemm.cu
+// gemm_nt_persist_kernel) with its SM filter exposed, so that tests can force every placement case -- all CTAs
+// admitted (sm_first = 0), a single SM admitted, none admitted (the last CTA to leave then does all the work).
+// batch2 products: pair b uses A + b stride2A, B + b stride2B, C + b stride2C.
+int gpmp_debug_gemm_nt_persist(const double* A_dev, long long lda, const double* B_dev, long long ldb, double* C_dev,
+                               long long ldc, int M, int N, int K, double alpha, double beta, int tri, int lower,
+                               int batch2, long long stride2A, long long stride2B, long long stride2C, int sm_first,
+                               void* stream) {
+    if (!A_dev || !B_dev || !C_dev || M < 0 || N < 0 || K < 0 || tri < 0 || tri > 4 || batch2 < 1) return GPMP_ERR_ARG;
+    GemmDesc g = gemm_desc();
+    g.A = A_dev; g.lda = lda; g.B = B_dev; g.ldb = ldb; g.C = C_dev; g.ldc = ldc;
+    g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.krange = tri; g.lower = lower ? 1 : 0;
+    g.reverse = (tri == KR_TO_ROW);
+    g.batch2 = batch2; g.stride2A = stride2A; g.stride2B = stride2B; g.stride2C = stride2C;
+    return launch_gemm_nt_persist(g, (cudaStream_t)stream, sm_first);
+}
+
 // development hook: phase timestamps (clock64) of the diagonal-tile kernel; not declared in the header
 // development hook: phase clocks of the last stamped chain-step launch (GPMP_DEV_STAMPS=1), 64 values
 int gpmp_debug_chain_stamps(long long* out_host) { return debug_chain_stamps(out_host); }

@@ -157,6 +157,56 @@ def test_gemm_nt_machine_filling_shapes(gp, M, N, K, lower, tri):
     assert relerr_norm(out, ref) <= 1e-13
 
 
+@pytest.mark.parametrize("sm_first", [0, 40, 147, 1000])
+@pytest.mark.parametrize("M,N,K,lower,tri,pairs", [(1100, 900, 300, False, 0, 1), (1024, 1024, 1024, True, 1, 1),
+                                                   (512, 512, 512, False, 1, 3), (2048, 2048, 130, True, 0, 1)])
+def test_gemm_nt_persistent_any_placement(gp, M, N, K, lower, tri, pairs, sm_first):
+    """The persistent form of the NT GEMM (gemm.cu gemm_nt_persist_kernel: the levels of T = L^-1 that run under the
+    tail of a factorisation): CTAs on SMs below sm_first leave at once, the others draw (tile, pair) indices from a
+    counter, the last CTA to leave finishes what is left.  The result must not depend on placement: every CTA
+    admitted (0), most (40), a single SM (147), none at all (1000: the last CTA does all the work)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(M + N + K + pairs)
+    ops = gp.ops
+    A = rng.standard_normal((pairs, M, K))
+    B = rng.standard_normal((pairs, N, K))
+    C0 = rng.standard_normal((pairs, M, N))
+    if tri == 1:
+        rows = (np.arange(M) // 128 * 128)[:, None]
+        keep = np.arange(K)[None, :] >= rows
+        Aj = np.where(keep, A, 7.0)  # junk left of the tile grid must be skipped
+        A = np.where(keep, A, 0.0)
+    else:
+        Aj = A
+    ldk, ldn = (K + 15) // 16 * 16, (N + 15) // 16 * 16
+    Ad = torch.zeros((pairs, M, ldk), dtype=torch.float64, device="cuda")
+    Bd = torch.zeros((pairs, N, ldk), dtype=torch.float64, device="cuda")
+    Cd = torch.zeros((pairs, M, ldn), dtype=torch.float64, device="cuda")
+    Ad[:, :, :K] = torch.as_tensor(Aj)
+    Bd[:, :, :K] = torch.as_tensor(B)
+    Cd[:, :, :N] = torch.as_tensor(C0)
+    lib = gp._abi.lib()
+    fn = lib.gpmp_debug_gemm_nt_persist
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                   C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
+                   C.c_longlong, C.c_int, C.c_void_p]
+    for _ in range(2):  # twice: the counter pair must come back reset
+        Cd[:, :, :N] = torch.as_tensor(C0)
+        rc = fn(Ad.data_ptr(), ldk, Bd.data_ptr(), ldk, Cd.data_ptr(), ldn, M, N, K, -0.5, 2.0, tri, int(lower), pairs,
+                M * ldk, N * ldk, M * ldn, sm_first, gp._abi.stream_ptr())
+        assert rc == 0
+        out = Cd[:, :, :N].cpu().numpy()
+        ref = -0.5 * np.einsum("pmk,pnk->pmn", A, B) + 2.0 * C0
+        if lower:
+            r, c = np.arange(M)[:, None], np.arange(N)[None, :]
+            untouched, visited = (c // 64 > r // 64)[None], (c // 64 <= r // 64)[None]
+            assert np.array_equal(out[np.broadcast_to(untouched, out.shape)], C0[np.broadcast_to(untouched, out.shape)])
+            out, ref = np.where(visited, out, 0.0), np.where(visited, ref, 0.0)
+        assert relerr_norm(out, ref) <= 1e-13
+
+
 @pytest.mark.parametrize("n", [1, 6, 64, 127, 128, 129, 300, 700, 1500, 2500])
 def test_potrf_potri_trsm(gp, n):
     rng = np.random.default_rng(n)
