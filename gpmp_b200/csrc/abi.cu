@@ -525,14 +525,21 @@ int gpmp_lik_grad(const gpmp_cov_spec* spec, const double* x_dev, int n, int q, 
     double* Tup = (double*)(base + w.off_Tup);
     double* Kinv = (double*)(base + w.off_Kinv);
     double* U = (double*)(base + w.off_U);
+    // U = [Q~; r] T needs only T: it runs on a library-owned side stream under the K^-1 = T^T T product
+    BatchStreams* bs = (n >= 2048 && prof().enabled != 2) ? batch_streams(s) : nullptr;
+    const bool side = bs && bs->ok;
     int rc = potri_core(A, n, w.lda, w.pw.NB, (const double*)(pb + w.pw.off_tlo), (const double*)(pb + w.pw.off_tup),
-                        Tlo, Tup, Kinv, w.lda, s, 1, 0, 0, 0, early_get(base));
+                        Tlo, Tup, Kinv, w.lda, s, 1, 0, 0, 0, early_get(base), side ? bs->fork : nullptr);
     if (rc) return rc;
+    cudaStream_t su = side ? bs->q[0] : s;
+    if (side && cudaStreamWaitEvent(su, bs->fork, 0) != cudaSuccess) return GPMP_ERR_CUDA;
     URowsArgs u;
     u.R = A + (long long)n * w.lda; u.ldr = w.lda; u.r = w.r; u.Tup = Tup; u.ldt = w.lda; u.U = U; u.ldu = w.lda;
     u.n = n; u.j0 = 0; u.j1 = 0;
-    rc = launch_urows(u, s);
+    rc = launch_urows(u, su);
     if (rc) return rc;
+    if (side && (cudaEventRecord(bs->join[0], su) != cudaSuccess || cudaStreamWaitEvent(s, bs->join[0], 0) != cudaSuccess))
+        return GPMP_ERR_CUDA;
     if (spec) {
         rc = launch_contract(spec, x_dev, n, nullptr, n, Kinv, w.lda, U, w.lda, w.r, 1, 0, 0.5, grad_dev,
                              base + w.off_partial, w.total_grad - w.off_partial, s);

@@ -50,7 +50,9 @@ int potrf_core(double* A, long long lda, long long strideA, int n, int nrows, in
 // matrix (ceil(n / 128) for the look-ahead path of a single matrix, 1 for the batched value-only path)
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
                double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream, int batch = 1,
-               long long strideL = 0, long long strideTc = 0, long long strideT = 0, int prefix = 0);
+               long long strideL = 0, long long strideTc = 0, long long strideT = 0, int prefix = 0,
+               cudaEvent_t t_done = nullptr);
+// t_done: recorded on the stream once T is complete (before the K^-1 product)
 // prefix: the leading prefix x prefix block of T is already complete (EarlyInverse)
 int trsm_rows_core(const double* A, int n, long long lda, int NB, const double* Tlo_c, const double* Tup_c,
                    double* Bt, int m, long long ldb, int trans, double* W, cudaStream_t stream,

@@ -2229,7 +2229,7 @@ int dist_finish(double* A, long long lda, int n, int nrows, int NB, double* Tlo,
 // ---- potri: Tlo/Tup (n x n) from L and the compact NB-block inverses, then Kinv = T^T T (lower) ----
 int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_c, const double* Tup_c,
                double* Tlo, double* Tup, double* Kinv, long long ldk, cudaStream_t stream, int batch,
-               long long strideL, long long strideTc, long long strideT, int prefix) {
+               long long strideL, long long strideTc, long long strideT, int prefix, cudaEvent_t t_done) {
     // batched form: entry b reads L + b strideL and the compact inverses + b strideTc, and writes Tlo / Tup / Kinv
     // + b strideT (all three share one stride)
     if (n <= 0 || batch <= 0) return GPMP_OK;
@@ -2252,6 +2252,8 @@ int potri_core(const double* L, int n, long long ldl, int NB, const double* Tlo_
                             pair0);
         if (rc) return rc;
     }
+    // T is complete: work that needs only T (the U rows of the gradient) may start on another stream now
+    if (t_done && cudaEventRecord(t_done, stream) != cudaSuccess) return GPMP_ERR_CUDA;
     // Kinv (lower) = T^T T :  Kinv_ij = sum_{k >= i} Tup[i][k] Tup[j][k]
     GemmDesc g = gemm_desc();
     g.A = Tup; g.lda = ldk; g.strideA = strideT; g.B = Tup; g.ldb = ldk; g.strideB = strideT;
