@@ -14,6 +14,7 @@
 // Shared tiles are dense 128-byte rows with the 16-byte chunk index XOR-swizzled by (row & 7) -- the
 // layout a TMA SWIZZLE_128B box produces.  Inside a K chunk the k index is permuted (lane kk owns
 // k = 4*kk + s at MMA step s) so each lane fetches its 4 steps with two conflict-free LDS.128.
+#include <atomic>
 #include "common.cuh"
 
 namespace gpmp {
@@ -303,7 +304,7 @@ int launch_gemm_nt_persist(const GemmDesc& g, cudaStream_t stream, int sm_first)
     using Cfg = GemmCfg<2, 2, 4, 4, 3, 1>;
     auto kern = gemm_nt_persist_kernel<2, 2, 4, 4, 4, 3, 1>;
     static unsigned long long configured = 0;
-    static unsigned int next_slot = 0;
+    static std::atomic<unsigned int> next_slot{0};  // (two host threads must never draw the same counter pair)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((configured >> (dev & 63)) & 1ull)) {
@@ -331,7 +332,7 @@ int launch_gemm_nt_persist(const GemmDesc& g, cudaStream_t stream, int sm_first)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned int grid = (unsigned int)(total < 4LL * sms ? total : 4LL * sms);
-    const int slot = (int)(next_slot++ & 1023u);  // (a slot is reused 1024 persistent launches later)
+    const int slot = (int)(next_slot.fetch_add(1u) & 1023u);  // (a slot is reused 1024 persistent launches later)
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(a, (int)ntiles, slot, sm_first);
     GPMP_CHECK_LAUNCH();
     return GPMP_OK;
