@@ -413,7 +413,7 @@ def run_gpu(args):
         "frac": achieved / dmma_peak, "traffic": traffic,
         "traffic_note": (f"dram__bytes_read+write summed over all DMMA launches of one evaluation ({traffic_src})"
                          if traffic_src else "no committed ncu capture found"),
-        "kernel": "gpmp::gemm_nt_kernel (FP64 DMMA.8x8x4)",
+        "kernel": "gpmp::gemm_nt_tma_kernel + gpmp::gemm_nt_kernel (FP64 DMMA.8x8x4; the TMA / mbarrier 128x128 kernel for the long-k products, the cp.async 64x64 kernel for the K = 512 updates)",
         "peak_source": "FP64 tensor pipe issue rate measured in this run (gpmp_measure_dmma_peak: 148x8 CTAs x 16 warps "
                        "x 8 independent DMMA.8x8x4 chains from registers, best of 10); MEASURED_PEAKS.json has no fp64 "
                        "entry",
