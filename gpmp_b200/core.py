@@ -17,6 +17,7 @@ Two ways in, chosen per call from what the user's covariance callable returns:
 """
 from __future__ import annotations
 
+import math
 import warnings
 
 import numpy as np
@@ -276,30 +277,34 @@ class Model:
 
     # ------------------------------------------------------------------ sample paths
     def sample_paths(self, xt, nb_paths, method="chol", check_result=True):
-        """nb_paths draws of GP(0, k) at xt: C @ N(0, I) with K(xt, xt) = C C^T (core/sample_paths.py:18-63).
-        Only the Cholesky route exists on the device: method='svd' (the symmetric square root U sqrt(s) U^T,
-        :50-58, meant for covariance matrices Cholesky cannot factor) is refused loudly, not emulated.
-        check_result=True raises when K(xt, xt) is not positive definite (the reference's NaN check, :46-49);
-        False skips the device->host read of the status word and returns whatever the factorisation produced."""
-        if method != "chol":
-            if method == "svd":
-                raise _abi.GpmpError("sample_paths(method='svd') has no device implementation; use 'chol'")
+        """nb_paths draws of GP(0, k) at xt: C @ N(0, I) (core/sample_paths.py:18-63).
+        method='chol': K(xt, xt) = C C^T by the device Cholesky; check_result=True raises when K is not positive
+        definite (the reference's NaN check, :46-49), False skips the device->host read of the status word.
+        method='svd' (:50-58, for covariance matrices Cholesky cannot factor): C = U sqrt(s) U^T, the symmetric
+        square root of K -- computed here without an eigensolver, by the coupled Newton-Schulz iteration on the
+        DMMA GEMM (see _symmetric_sqrt)."""
+        if method not in ("chol", "svd"):
             raise ValueError("method must be 'chol' or 'svd'")
         xt_ = ops.to_device(xt)
         normals = torch.randn(xt_.shape[0], nb_paths, dtype=torch.float64, device=xt_.device,
                               generator=_generator())
-        return self.sample_paths_from_normals(xt_, normals, check_result=check_result)
+        return self.sample_paths_from_normals(xt_, normals, check_result=check_result, method=method)
 
-    def sample_paths_from_normals(self, xt, normals, check_result=True):
+    def sample_paths_from_normals(self, xt, normals, check_result=True, method="chol"):
         """Deterministic part of sample_paths: C @ normals (the map parity is defined on)."""
+        if method not in ("chol", "svd"):
+            raise ValueError("method must be 'chol' or 'svd'")
         xt_ = ops.to_device(xt)
         normals = ops.to_device(normals)
         with torch.no_grad():
             K = kernel.materialize(self.covariance(xt_, xt_, _as_param(self.covparam)))
+            Nt = ops.transpose(normals)  # paths x nt
+            if method == "svd":
+                Croot = _symmetric_sqrt(K)  # symmetric: C @ normals = (normals^T C)^T
+                return ops.transpose(ops.gemm_nt(Nt, Croot)).contiguous()
             fac = ops.potrf(K, check_pd=bool(check_result))  # LinAlgError when not PD and checked
             nt = fac.n
             L = fac.A[:nt, :nt]
-            Nt = ops.transpose(normals)  # paths x nt
             return ops.gemm_nt(L, Nt, tri=_abi.TRI_A_LOWER).contiguous()
 
     def conditional_sample_paths(self, ztsim, xi_ind, zi, xt_ind, lambda_t, convert_out=True):
@@ -489,3 +494,41 @@ def _generator():
 
 def set_seed(seed):
     _generator().manual_seed(int(seed))
+
+
+def _symmetric_sqrt(K, max_iter=120):
+    """Symmetric (principal) square root of a symmetric positive SEMI-definite matrix on the device -- what the
+    reference's U sqrt(s) V^T of gnp.svd(K, hermitian=True) is (core/sample_paths.py:50-55) -- by the coupled
+    Newton-Schulz iteration, which needs nothing but products (three DMMA GEMMs per step):
+
+        Y0 = K / ||K||_F,  Z0 = I,   W = 3 I - Z Y,   Y <- Y W / 2,   Z <- W Z / 2,      sqrt(K) = sqrt(||K||_F) lim Y.
+
+    The ORDER of the factors matters for stability (Y W and W Z, never Y W^T or W Z^T: in floating point the iterates
+    are only nearly symmetric, and the transposed forms amplify that defect), so the second operand of every NT
+    product is transposed explicitly first (n^2 against the product's n^3).
+    Eigenvalues of K / ||K||_F lie in [0, 1]: the iteration converges for all of them (zero stays zero); a direction
+    of relative size lambda needs about log_1.5(lambda^-1/2) steps, after which convergence is quadratic.  Z tends
+    to the INVERSE root, which does not exist for a singular K, so rounding noise in the null directions eventually
+    grows: the step with the smallest change of Y is kept (on singular test matrices -- duplicated points, dense
+    1-d designs with cond ~ 5e17: C C^T = K to 2e-8 ||K||, paths within 1e-7 of those of the SVD root, the size of the
+    sqrt(eps) noise both carry in the null space; well-conditioned matrices converge to rounding)."""
+    n = K.shape[0]
+    scale = float(torch.linalg.norm(K))
+    if not (scale > 0.0):
+        return K.clone()
+    eye3 = 3.0 * torch.eye(n, dtype=torch.float64, device=K.device)
+    Y = ops.padded(K / scale)
+    Z = ops.padded(torch.eye(n, dtype=torch.float64, device=K.device))
+    best, best_Y, best_it = float("inf"), Y, 0
+    for it in range(max_iter):
+        W = ops.padded(eye3)
+        ops.gemm_nt(Z, ops.transpose(Y), C_out=W, alpha=-1.0, beta=1.0)   # W = 3 I - Z Y
+        Yn = ops.gemm_nt(Y, ops.transpose(W), alpha=0.5)                   # Y W / 2
+        Z = ops.gemm_nt(W, ops.transpose(Z), alpha=0.5)                    # W Z / 2
+        change = float(torch.linalg.norm(Yn - Y) / torch.linalg.norm(Yn))
+        Y = Yn
+        if change < best:
+            best, best_Y, best_it = change, Y, it
+        if change < 1e-15 or (change > 4.0 * best and it > best_it + 1):
+            break
+    return ops.padded(math.sqrt(scale) * best_Y)

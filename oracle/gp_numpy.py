@@ -385,6 +385,14 @@ def sample_paths_from_normals(model, xt, normals):
     return C @ normals
 
 
+def sample_paths_svd_from_normals(model, xt, normals):
+    """Deterministic part of core/sample_paths.py:50-58 ('svd' branch): C @ normals with the symmetric square root
+    C = (U sqrt(s)) V^T of K(xt, xt) from gnp.svd(K, hermitian=True) (numpy_backend: numpy.linalg.svd)."""
+    K = model.covariance(xt, xt, model.covparam)
+    U, s, Vt = np.linalg.svd(K, full_matrices=True, hermitian=True)
+    return ((U * np.sqrt(s)) @ Vt) @ normals
+
+
 def conditional_sample_paths(ztsim, xi_ind, zi, xt_ind, lambda_t):
     """core/sample_paths.py:66-119."""
     zi_ = np.asarray(zi).reshape(-1, 1)

@@ -89,8 +89,8 @@ def test_sample_paths_method_and_check_result(gp):
     model = gp.core.Model(None, _cov(gp, 2), None, th, "zero")
     zs = model.sample_paths(x, 7, method="chol", check_result=True)
     assert tuple(zs.shape) == (n, 7) and bool(torch.isfinite(zs).all())
-    with pytest.raises(gp._abi.GpmpError):
-        model.sample_paths(x, 3, method="svd")
+    zs2 = model.sample_paths(x, 3, method="svd")
+    assert tuple(zs2.shape) == (n, 3) and bool(torch.isfinite(zs2).all())
     with pytest.raises(ValueError):
         model.sample_paths(x, 3, method="qr")
     # a covariance that is not positive definite: raises when checked, returns (non-finite paths) when not
@@ -100,3 +100,32 @@ def test_sample_paths_method_and_check_result(gp):
         bad.sample_paths(x, 2, check_result=True)
     out = bad.sample_paths(x, 2, check_result=False)
     assert tuple(out.shape) == (n, 2)
+
+
+@pytest.mark.parametrize("name", ["svd_dup_n200_d2_p2", "svd_dense_n300_d1_p2", "svd_pd_n120_d3_p1"])
+def test_sample_paths_svd_route_matches_reference(gp, name):
+    """sample_paths(method="svd") (core/sample_paths.py:50-58): the symmetric square root U sqrt(s) V^T of K(xt, xt)
+    times fixed normals, against the reference's own lines run on GPmp (oracle/make_golden_svd.py).  The two singular
+    cases (duplicated points: the Cholesky route fails; a dense 1-d design, cond ~ 5e17) carry sqrt(eps)-sized noise
+    in the null space in BOTH implementations, so they are held to 2e-6 of the scale of the paths and to
+    C C^T = K at 2e-7 (CPU emulation of the same iteration: 1e-7 / 2e-8); the well-conditioned case to 1e-10 / 1e-12."""
+    z = np.load(os.path.join(GOLDEN_DIR, "reference_svd.npz"))
+    g = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+    x, th, p, normals = g["x"], g["theta"], int(g["p"]), g["normals"]
+    model = gp.core.Model(None, _cov(gp, p), None, th, "zero")
+    zs = model.sample_paths_from_normals(x, normals, method="svd").cpu().numpy()
+    scale = float(np.max(np.abs(g["zsim"])))
+    err = float(np.max(np.abs(zs - g["zsim"]))) / scale
+    singular = float(g["s"][0] / max(g["s"][-1], 1e-300)) > 1e12
+    # the root itself: C = paths of the identity; C C^T must reproduce K
+    C = model.sample_paths_from_normals(x, np.eye(x.shape[0]), method="svd").cpu().numpy()
+    K = gp.kernel.maternp_covariance(gp.num.asarray(x), gp.num.asarray(x), p, th).cpu().numpy()
+    back = float(np.max(np.abs(C @ C.T - K)) / np.max(np.abs(K)))
+    print(f"[parity] {name}: paths vs reference {err:.2e} of scale, C C^T vs K {back:.2e}, "
+          f"C vs reference root {np.max(np.abs(C - g['C'])) / np.max(np.abs(g['C'])):.2e}")
+    assert err <= (2e-6 if singular else 1e-10)
+    assert back <= (2e-7 if singular else 1e-12)
+    assert np.max(np.abs(C - C.T)) <= (1e-6 if singular else 1e-12) * np.max(np.abs(C))
+    if name.startswith("svd_dup"):
+        with pytest.raises(torch.linalg.LinAlgError):
+            model.sample_paths_from_normals(x, normals, method="chol", check_result=True)
