@@ -16,11 +16,14 @@
 // and the trailing matrix gets ONE K=NB SYRK (lower tiles).  Extra rows n..nrows-1 ride along in every
 // solve (they leave as B L^-T).  The NB-wide inverses of the diagonal blocks, which the triangular inverse
 // and the row solves start from, are assembled afterwards by block doubling
-// (inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1,C^-1]]).  Single large matrices run a three-stream
-// look-ahead (potrf_core) whose chain uses the factor-only tile kernel and the substitution solve
-// (trsm_tile_kernel) instead of the tile inverse; batched value-only sweeps use the packed factor-only tile
-// kernel (two tiles per SM) and one solve CTA per matrix; the same pieces serve the panel-partitioned
-// multi-GPU loop (dist_*).
+// (inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1,C^-1]]).  Single large matrices run a multi-stream
+// look-ahead (potrf_core, depth 4) whose chain is ONE fused launch per 128-column step (chain_step_kernel: solve
+// of the rows below, in-group updates and factorisation of the next tile, with flags in global memory between
+// its CTAs) for groups of full tiles, and the factor-only tile kernel + substitution solve (trsm_tile_kernel) +
+// K = 128 GEMM otherwise; with the gradient's buffers at hand the leading block of T = L^-1 is computed under the
+// latency-bound tail of the factorisation (early_inverse: persistent GEMMs that keep off the chain's SMs).
+// Batched value-only sweeps use the packed factor-only tile kernel (two tiles per SM) and one solve CTA per
+// matrix; the same pieces serve the panel-partitioned multi-GPU loop (dist_*).
 #include <cstdlib>
 #include <mutex>
 #include <vector>
