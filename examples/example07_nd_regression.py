@@ -3,12 +3,15 @@ composed by the user from the gnp primitives (the covariance of GPmp's examples/
 95-130), REML selection by SciPy's SLSQP with GPmp's options (kernel/parameter_selection.py:236-253) on the device
 criterion, prediction on held-out points.  A user-composed covariance takes the composable path: the distance
 and Matern ops build K on the device and the likelihood op hands dvalue/dK back to autograd."""
+import os
+import sys
 import time
 
 import numpy as np
 import torch
 from scipy.optimize import minimize
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a source checkout
 import gpmp_b200 as gp
 
 gnp = gp.num
