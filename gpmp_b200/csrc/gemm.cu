@@ -215,19 +215,30 @@ __global__ void __launch_bounds__(WM* WN * 32, MINB) gemm_nt_kernel(const GemmKA
 
 // Persistent form for products that must leave part of the machine to other work (the triangular-inverse levels
 // that run under the tail of a factorisation, potrf.cu): CTAs that find themselves on an SM below `sm_first` exit at
-// once; the others draw (tile, pair) indices from a counter in global memory until the list is exhausted.  The last
-// CTA to leave resets the counter pair for its next user.
-__device__ unsigned int g_gemm_counters[2 * 1024];
+// once; the others draw (tile, pair) indices from a counter in global memory until the list is exhausted.  If half
+// of the grid has arrived and still nobody has drawn a tile (other kernels keep the admitted SMs full while the
+// avoided ones are free, so the scheduler sends the whole grid there to exit), the CTAs that arrive from then on
+// work wherever they land, and the last CTA to leave finishes whatever is left and resets the counters for their
+// next user: progress and correctness never depend on placement.  (Measured: letting the first 16 CTAs work
+// unconditionally instead costs the headline 0.1-0.25 ms -- they land exactly on the SMs kept free for the chain.)
+__device__ unsigned int g_gemm_counters[3 * 1024];
 template <int WM, int WN, int MI, int NI, int MINB, int STAGES, int SUBK>
 __global__ void __launch_bounds__(WM* WN * 32, MINB)
 gemm_nt_persist_kernel(const GemmKArgs a, int ntiles, int slot, int sm_first) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned int next;
-    unsigned int* ctr = g_gemm_counters + 2 * slot;
+    unsigned int* ctr = g_gemm_counters + 3 * slot;
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     const unsigned int total = (unsigned int)ntiles * (unsigned int)a.g.batch2;
-    if ((int)smid >= sm_first) {
+    __shared__ unsigned int admitted;  // decided by ONE thread: the whole CTA must take the same branch
+    if (threadIdx.x == 0) {
+        const unsigned int order = atomicAdd(&ctr[2], 1u);  // arrival order of this CTA
+        const bool stranded = order >= gridDim.x / 2 && *reinterpret_cast<volatile unsigned int*>(&ctr[0]) == 0u;
+        admitted = ((int)smid >= sm_first || stranded) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (admitted) {
         for (;;) {
             __syncthreads();  // the previous tile's shared memory and `next` are no longer read
             if (threadIdx.x == 0) next = atomicAdd(&ctr[0], 1u);
@@ -260,6 +271,7 @@ gemm_nt_persist_kernel(const GemmKArgs a, int ntiles, int slot, int sm_first) {
     if (threadIdx.x == 0) {
         ctr[0] = 0u;
         ctr[1] = 0u;
+        ctr[2] = 0u;
         __threadfence();
     }
 }

@@ -163,8 +163,9 @@ def test_gemm_nt_machine_filling_shapes(gp, M, N, K, lower, tri):
 def test_gemm_nt_persistent_any_placement(gp, M, N, K, lower, tri, pairs, sm_first):
     """The persistent form of the NT GEMM (gemm.cu gemm_nt_persist_kernel: the levels of T = L^-1 that run under the
     tail of a factorisation): CTAs on SMs below sm_first leave at once, the others draw (tile, pair) indices from a
-    counter, the last CTA to leave finishes what is left.  The result must not depend on placement: every CTA
-    admitted (0), most (40), a single SM (147), none at all (1000: the last CTA does all the work)."""
+    counter; when half the grid has arrived and nobody has drawn a tile yet, the CTAs arriving from then on work
+    wherever they land, and the last CTA to leave finishes what is left.  The result must not depend on placement:
+    every CTA admitted (0), most (40), a single SM (147), none at all (1000: the stranded-grid rule does the work)."""
     import ctypes as C
 
     rng = np.random.default_rng(M + N + K + pairs)
