@@ -128,7 +128,8 @@ class DrivenSweeps:
 
         sweeps = DrivenSweeps(crit, dim, group)       # crit: BatchedCriterion(..., group=group)
         if rank != 0: sweeps.serve()                  # returns when rank 0 calls sweeps.stop()
-        else: ...sampler calling sweeps(thetas)...; sweeps.stop()
+        else:
+            with sweeps: ...sampler calling sweeps(thetas)...      # stop() on exit, also when the sampler raises
     """
 
     def __init__(self, fn, dim, group=None, device=None):
@@ -137,6 +138,7 @@ class DrivenSweeps:
         self.device = torch.device(device) if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
         self.src = td.get_global_rank(group, 0) if (group is not None and self.size > 1) else 0
+        self._stopped = False
 
     def __call__(self, rows):
         import numpy as np
@@ -166,5 +168,14 @@ class DrivenSweeps:
         return served
 
     def stop(self):
-        if self.size > 1 and self.rank == 0:
+        if self.size > 1 and self.rank == 0 and not self._stopped:
+            self._stopped = True
             td.broadcast(torch.tensor([-1], dtype=torch.int64, device=self.device), src=self.src, group=self.group)
+
+    # `with DrivenSweeps(...) as sweeps:` on rank 0 releases the serving ranks even if the sampler raises
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        self.stop()
+        return False

@@ -76,10 +76,14 @@ def _driven_worker(rank, world, port, q):
     else:
         rng = np.random.default_rng(os.getpid())  # only rank 0 draws: the ranks need not be in lock step
         ok = True
-        for N in (7, 1, 12, 5):  # the particle count changes from sweep to sweep (rows outside the box are dropped)
-            rows = rng.standard_normal((N, 3))
-            ok = ok and np.allclose(sweeps(rows), (rows ** 2).sum(axis=1), rtol=0, atol=1e-15)
-        sweeps.stop()
+        try:
+            with sweeps:  # releases the serving rank on exit, also when the driver raises
+                for N in (7, 1, 12, 5):  # the particle count changes from sweep to sweep (rows outside the box are dropped)
+                    rows = rng.standard_normal((N, 3))
+                    ok = ok and np.allclose(sweeps(rows), (rows ** 2).sum(axis=1), rtol=0, atol=1e-15)
+                raise RuntimeError("sampler failed")
+        except RuntimeError:
+            pass
         q.put(("driver", ok))
     dist.destroy_process_group()
 
